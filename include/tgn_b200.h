@@ -1,0 +1,143 @@
+/*
+ * tgn_b200.h -- C ABI of libtgn_b200.so: the B200-native (sm_100a) replacement for the native
+ * layer of limhoyeon/ToothGroupNetwork's point-cloud operator hot path.
+ *
+ * Boundary being replaced (paths relative to /root/reference/external_libs/pointops/src):
+ * the reference exposes its kernels to the pybind glue through ten `extern "C"` launchers
+ * taking raw device pointers.  Part 1 below exports those ten symbols with identical
+ * signatures and semantics (legacy default stream, void return, caller-owned outputs), so
+ * the reference's `*_cuda.cpp` glue links against this library unchanged.  Part 2 is the
+ * same operations with an explicit stream and a status code, plus the operations the
+ * reference runs as PyTorch tensor code on the pointnet2 side (ball query, 3-NN, gather,
+ * grouped shared-MLP set abstraction), which this library provides as fused kernels.
+ *
+ * Conventions: all pointers are DEVICE pointers unless stated otherwise; float = fp32,
+ * int = int32; tensors are dense row-major; `stream` is a cudaStream_t passed as void*.
+ * Part-2 functions return 0 on success, TGN_ERR_* otherwise (text in tgn_last_error()).
+ * No function synchronises the device.  There is no CPU path.
+ */
+#ifndef TGN_B200_H_
+#define TGN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================================
+ * Part 1 -- drop-in for the reference's extern "C" launchers.
+ * =================================================================================== */
+
+/* sampling/sampling_cuda_kernel.h:14 (definition sampling_cuda_kernel.cu:131-171).
+ * b clouds packed in xyz (n_total,3) with cumulative ends offset[b]; new_offset[b] cumulative
+ * sample counts; n = largest cloud size (selects the reference's block size and therefore its
+ * tie-break); tmp (n_total) pre-filled by the caller (1e10), holds the running minima on
+ * return; idx (m_total) receives global row ids, first sample of a cloud = its first point. */
+void furthestsampling_cuda_launcher(int b, int n, const float *xyz, const int *offset,
+                                    const int *new_offset, float *tmp, int *idx);
+
+/* knnquery/knnquery_cuda_kernel.h:14 (definition knnquery_cuda_kernel.cu:111-116).
+ * idx (m,nsample), dist2 (m,nsample) = squared distances, ascending; a segment with fewer
+ * than nsample points leaves (segment start, 1e10) in the trailing slots. */
+void knnquery_cuda_launcher(int m, int nsample, const float *xyz, const float *new_xyz,
+                            const int *offset, const int *new_offset, int *idx, float *dist2);
+
+/* grouping/grouping_cuda_kernel.h:13-14 (grouping_cuda_kernel.cu:27-41) */
+void grouping_forward_cuda_launcher(int m, int nsample, int c, const float *input, const int *idx, float *output);
+void grouping_backward_cuda_launcher(int m, int nsample, int c, const float *grad_output, const int *idx, float *grad_input);
+
+/* interpolation/interpolation_cuda_kernel.h:13-14 (interpolation_cuda_kernel.cu:35-47);
+ * output / grad_input are accumulated into and must be pre-zeroed by the caller. */
+void interpolation_forward_cuda_launcher(int n, int c, int k, const float *input, const int *idx, const float *weight, float *output);
+void interpolation_backward_cuda_launcher(int n, int c, int k, const float *grad_output, const int *idx, const float *weight, float *grad_input);
+
+/* subtraction/subtraction_cuda_kernel.h:13-14 (subtraction_cuda_kernel.cu:32-44) */
+void subtraction_forward_cuda_launcher(int n, int nsample, int c, const float *input1, const float *input2, const int *idx, float *output);
+void subtraction_backward_cuda_launcher(int n, int nsample, int c, const int *idx, const float *grad_output, float *grad_input1, float *grad_input2);
+
+/* aggregation/aggregation_cuda_kernel.h:12-17 (aggregation_cuda_kernel.cu:41-53) */
+void aggregation_forward_cuda_launcher(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                                       const float *weight, const int *idx, float *output);
+void aggregation_backward_cuda_launcher(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                                        const float *weight, const int *idx, const float *grad_output,
+                                        float *grad_input, float *grad_position, float *grad_weight);
+
+/* ===================================================================================
+ * Part 2 -- stream-taking, status-returning entry points.
+ * =================================================================================== */
+#define TGN_OK 0
+#define TGN_ERR_INVALID 1
+#define TGN_ERR_CUDA 2
+
+int tgn_version(void);
+const char *tgn_last_error(void);          /* thread-local, valid until the next failing call */
+int tgn_launch_count(void);                /* kernels launched by this library in this process */
+
+/* FPS.  Same contract as furthestsampling_cuda_launcher; tmp may be NULL (running minima start
+ * at 1e10 and are not written back) when the cloud fits the register-resident kernel.
+ * `mode`: 0 = choose by b and n (throughput when b is large, latency when small),
+ *         otherwise force a cluster size (1,2,4,8) or the streaming kernel (-1). */
+int tgn_furthestsampling(int b, int n_max, const float *xyz, const int *offset, const int *new_offset,
+                         float *tmp, int *idx, int mode, void *stream);
+
+/* kNN.  b = number of segments (length of offset / new_offset). */
+int tgn_knnquery(int b, int m, int nsample, const float *xyz, const float *new_xyz, const int *offset,
+                 const int *new_offset, int *idx, float *dist2, void *stream);
+
+int tgn_grouping_forward(int m, int nsample, int c, const float *input, const int *idx, float *output, void *stream);
+int tgn_grouping_backward(int m, int nsample, int c, const float *grad_output, const int *idx, float *grad_input, void *stream);
+int tgn_interpolation_forward(int n, int c, int k, const float *input, const int *idx, const float *weight, float *output, void *stream);
+int tgn_interpolation_backward(int n, int c, int k, const float *grad_output, const int *idx, const float *weight, float *grad_input, void *stream);
+int tgn_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2, const int *idx, float *output, void *stream);
+int tgn_subtraction_backward(int n, int nsample, int c, const int *idx, const float *grad_output, float *grad_input1, float *grad_input2, void *stream);
+int tgn_aggregation_forward(int n, int nsample, int c, int w_c, const float *input, const float *position, const float *weight,
+                            const int *idx, float *output, void *stream);
+int tgn_aggregation_backward(int n, int nsample, int c, int w_c, const float *input, const float *position, const float *weight,
+                             const int *idx, const float *grad_output, float *grad_input, float *grad_position,
+                             float *grad_weight, void *stream);
+
+/* Ball query: pointnet2_utils.query_ball_point (external_libs/pointnet2_utils/pointnet2_utils.py:120-144).
+ * xyz (B,N,3), new_xyz (B,S,3) -> group_idx (B,S,nsample): the first nsample point indices in
+ * ascending order whose EXPANDED squared distance (-2ab + |a|^2 + |b|^2, evaluated in the
+ * reference's rounding order) is not > r2, padded with the first hit; N in every slot when the
+ * ball is empty.  r2 must be float32(radius**2).  idx64 != 0 writes int64 (the reference's
+ * dtype), else int32. */
+int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float *xyz, const float *new_xyz,
+                   void *group_idx, int idx64, void *stream);
+
+/* 3 nearest coarse points by the same expanded distance (pointnet2_utils.py:333-335):
+ * xyz1 (B,N,3) fine, xyz2 (B,S,3) coarse, S >= 3 -> dist (B,N,3) ascending, idx (B,N,3) int32. */
+int tgn_three_nn(int B, int N, int S, const float *xyz1, const float *xyz2, float *dist, int *idx, void *stream);
+
+/* Weighted 3-point interpolation (pointnet2_utils.py:337-340): weights 1/(dist+1e-8) normalised,
+ * points2 (B,S,C) point-major -> out (B,N,C). */
+int tgn_three_interpolate(int B, int N, int S, int C, const float *points2, const float *dist, const int *idx,
+                          float *out, void *stream);
+
+/* Batched row gather: pointnet2_utils.index_points (pointnet2_utils.py:44-61).
+ * points (B,N,C), idx (B,M) int32 -> out (B,M,C). */
+int tgn_gather_rows(int B, int N, int M, int C, const float *points, const int *idx, float *out, void *stream);
+
+/* (B,C,N) -> (B,N,C) and back (the reference permutes with torch; here one tiled kernel). */
+int tgn_transpose_cn(int B, int C, int N, const float *in, float *out, void *stream);
+
+/* Fused set-abstraction body: gather -> [xyz_rel | feats] -> L x (1x1 conv + bias + ReLU) -> max
+ * over the K neighbours, without materialising the grouped tensor
+ * (PointNetSetAbstraction.forward pointnet2_utils.py:213-239 / Msg :261-299, eval-mode BatchNorm
+ * folded into weight/bias by the caller).
+ *   xyz (B,N,3); feats (B,N,D) point-major or NULL (D = 0); new_xyz (B,S,3); group_idx (B,S,K) int32
+ *   xyz_first: 1 -> channels [xyz_rel, feats] (SSG, :169), 0 -> [feats, xyz_rel] (MSG, :285)
+ *   n_layers in [1,4]; channels[n_layers+1] HOST array, channels[0] = 3 + D; every width <= 128
+ *   weights[l] (C_{l+1}, C_l) row-major DEVICE, biases[l] (C_{l+1}) DEVICE; the two pointer arrays are HOST arrays
+ *   out: channel-first (B, out_c_total, S); this branch writes channels [out_c_offset, +C_last)
+ *   engine: 0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 3xTF32 tensor-core kernel. */
+int tgn_sa_group_mlp_max(int B, int N, int S, int K, int D, const float *xyz, const float *feats, const float *new_xyz,
+                         const int *group_idx, int xyz_first, int n_layers, const int *channels,
+                         const float *const *weights, const float *const *biases, float *out, int out_c_total,
+                         int out_c_offset, int engine, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGN_B200_H_ */

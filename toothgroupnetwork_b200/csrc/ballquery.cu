@@ -1,0 +1,219 @@
+// ballquery.cu -- ball query and 3-NN on the PointNet++ side, sm_100a.
+//
+// The reference has no kernel here: query_ball_point materialises an (S,N) fp32 distance
+// matrix through a K=3 matmul plus an (S,N) int64 index tensor and SORTS every row
+// (external_libs/pointnet2_utils/pointnet2_utils.py:120-144); PointNetFeaturePropagation
+// sorts an (N,S) matrix to take three entries (:333-335).  Here both are streaming scans with
+// coordinates staged through shared memory, and the ball query stops as soon as a query has
+// its nsample hits.
+//
+// Bit-exact membership: the distance is evaluated in the reference's EXPANDED form and
+// rounding order (probed against torch, see oracle/pointops_oracle.c):
+//      dot = ax*bx; dot = fma(ay,by,dot); dot = fma(az,bz,dot);
+//      d = -2*dot; d += |a|^2; d += |b|^2      with |p|^2 = (x*x + y*y) + z*z, unfused
+// and a point is a member iff !(d > r2), r2 = float32(radius**2).
+#include <algorithm>
+
+#include "common.cuh"
+#include "tgn_b200.h"
+
+namespace tgn {
+namespace {
+
+constexpr int kTile = 1024;   // points staged per shared-memory tile (16 KB as SoA x,y,z,|p|^2)
+
+__device__ __forceinline__ float sq_norm_unfused(float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+__device__ __forceinline__ float sq_dist_expanded(float ax, float ay, float az, float an, float bx, float by, float bz,
+                                                  float bn) {
+    float dot = __fmul_rn(ax, bx);
+    dot = __fmaf_rn(ay, by, dot);
+    dot = __fmaf_rn(az, bz, dot);
+    float d = __fmul_rn(-2.0f, dot);
+    d = __fadd_rn(d, an);
+    return __fadd_rn(d, bn);
+}
+
+// Stage points [base, base+cnt) of one cloud into shared SoA arrays (coalesced 12-byte reads).
+template <int THREADS>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ pts, int base, int cnt, float* sx, float* sy,
+                                           float* sz, float* sn)
+{
+    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+        const float x = __ldg(pts + 3 * static_cast<size_t>(base + i)), y = __ldg(pts + 3 * static_cast<size_t>(base + i) + 1),
+                    z = __ldg(pts + 3 * static_cast<size_t>(base + i) + 2);
+        sx[i] = x; sy[i] = y; sz[i] = z; sn[i] = sq_norm_unfused(x, y, z);
+    }
+}
+
+// One warp per query, WARPS queries of one cloud per CTA.  Lanes test 32 consecutive points per
+// step; __ballot + popc give each hit its rank in ascending index order.
+template <int WARPS, typename IdxT>
+__global__ void __launch_bounds__(WARPS * 32)
+ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                  IdxT* __restrict__ group_idx)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ float sx[kTile], sy[kTile], sz[kTile], sn[kTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * WARPS + warp;
+    const bool live = q < S;
+    const float* pts = xyz + 3 * static_cast<size_t>(b) * N;
+    float ax = 0.f, ay = 0.f, az = 0.f, an = 0.f;
+    IdxT* row = nullptr;
+    if (live) {
+        const float* a = new_xyz + 3 * (static_cast<size_t>(b) * S + q);
+        ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
+        an = sq_norm_unfused(ax, ay, az);
+        row = group_idx + (static_cast<size_t>(b) * S + q) * nsample;
+    }
+    int cnt = live ? 0 : nsample;     // dead warps count as finished
+    int first = N;                    // sentinel the reference leaves when the ball is empty
+    for (int base = 0; base < N; base += kTile) {
+        const int tile = min(kTile, N - base);
+        __syncthreads();              // previous tile fully consumed
+        stage_tile<WARPS * 32>(pts, base, tile, sx, sy, sz, sn);
+        __syncthreads();
+        if (cnt < nsample) {
+            for (int o = 0; o < tile && cnt < nsample; o += 32) {
+                const int i = o + lane;
+                bool hit = false;
+                if (i < tile) hit = !(sq_dist_expanded(ax, ay, az, an, sx[i], sy[i], sz[i], sn[i]) > r2);
+                const unsigned mask = __ballot_sync(FULL, hit);
+                if (mask) {
+                    if (cnt == 0) first = base + o + __ffs(mask) - 1;
+                    const int pos = cnt + __popc(mask & ((1u << lane) - 1));
+                    if (hit && pos < nsample) row[pos] = static_cast<IdxT>(base + i);
+                    cnt += __popc(mask);
+                }
+            }
+        }
+        if (__syncthreads_and(cnt >= nsample)) break;   // every query of this CTA is full
+    }
+    if (live) {
+        cnt = min(cnt, nsample);
+        for (int p = cnt + lane; p < nsample; p += 32) row[p] = static_cast<IdxT>(first);
+    }
+}
+
+// 3 nearest coarse points per fine point; one thread per fine point, coarse cloud in shared tiles.
+// Strict '<' keeps the lower index among equal distances.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+three_nn_kernel(int N, int S, const float* __restrict__ xyz1, const float* __restrict__ xyz2, float* __restrict__ dist,
+                int* __restrict__ idx)
+{
+    __shared__ float sx[kTile], sy[kTile], sz[kTile], sn[kTile];
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * THREADS + threadIdx.x;
+    const bool live = i < N;
+    float ax = 0.f, ay = 0.f, az = 0.f, an = 0.f;
+    if (live) {
+        const float* a = xyz1 + 3 * (static_cast<size_t>(b) * N + i);
+        ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
+        an = sq_norm_unfused(ax, ay, az);
+    }
+    float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
+    int i0 = 0, i1 = 0, i2 = 0;
+    const float* pts = xyz2 + 3 * static_cast<size_t>(b) * S;
+    for (int base = 0; base < S; base += kTile) {
+        const int tile = min(kTile, S - base);
+        __syncthreads();
+        stage_tile<THREADS>(pts, base, tile, sx, sy, sz, sn);
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int j = 0; j < tile; ++j) {
+                const float d = sq_dist_expanded(ax, ay, az, an, sx[j], sy[j], sz[j], sn[j]);
+                if (d < d2) {
+                    const int g = base + j;
+                    if (d < d0) { d2 = d1; i2 = i1; d1 = d0; i1 = i0; d0 = d; i0 = g; }
+                    else if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = g; }
+                    else { d2 = d; i2 = g; }
+                }
+            }
+        }
+    }
+    if (live) {
+        const size_t o = 3 * (static_cast<size_t>(b) * N + i);
+        dist[o] = d0; dist[o + 1] = d1; dist[o + 2] = d2;
+        idx[o] = i0; idx[o + 1] = i1; idx[o + 2] = i2;
+    }
+}
+
+// out[b,n,:] = sum_k w_k * points2[b, idx[b,n,k], :],  w = (1/(d+1e-8)) / sum (pointnet2_utils.py:337-340)
+__global__ void __launch_bounds__(256)
+three_interpolate_kernel(int N, int S, int C, const float* __restrict__ points2, const float* __restrict__ dist,
+                         const int* __restrict__ idx, float* __restrict__ out)
+{
+    const int b = blockIdx.y;
+    const size_t total = static_cast<size_t>(N) * C;
+    const float* p2 = points2 + static_cast<size_t>(b) * S * C;
+    for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int n = static_cast<int>(e / C), c = static_cast<int>(e % C);
+        const size_t o = 3 * (static_cast<size_t>(b) * N + n);
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(dist[o], 1e-8f)), r1 = __fdiv_rn(1.0f, __fadd_rn(dist[o + 1], 1e-8f)),
+                    r2 = __fdiv_rn(1.0f, __fadd_rn(dist[o + 2], 1e-8f));
+        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+        float acc = __fmul_rn(p2[static_cast<size_t>(idx[o]) * C + c], w0);
+        acc = __fadd_rn(acc, __fmul_rn(p2[static_cast<size_t>(idx[o + 1]) * C + c], w1));
+        acc = __fadd_rn(acc, __fmul_rn(p2[static_cast<size_t>(idx[o + 2]) * C + c], w2));
+        out[(static_cast<size_t>(b) * N + n) * C + c] = acc;
+    }
+}
+
+}  // namespace
+}  // namespace tgn
+
+extern "C" {
+
+int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz, const float* new_xyz, void* group_idx,
+                   int idx64, void* stream)
+{
+    using namespace tgn;
+    if (B <= 0 || S <= 0 || nsample <= 0) return TGN_OK;
+    if (N <= 0) { set_error("ball_query: N must be positive"); return TGN_ERR_INVALID; }
+    if (B > 65535) { set_error("ball_query: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // 16 queries per CTA when that still gives >= 2 waves, else 8 (small batches)
+    const bool wide = static_cast<long long>(B) * ((S + 15) / 16) >= 2LL * sm_count();
+    if (wide) {
+        dim3 grid((S + 15) / 16, B);
+        if (idx64) ball_query_kernel<16, long long><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
+        else ball_query_kernel<16, int><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx));
+    } else {
+        dim3 grid((S + 7) / 8, B);
+        if (idx64) ball_query_kernel<8, long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
+        else ball_query_kernel<8, int><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx));
+    }
+    return check_launch("ball_query_kernel");
+}
+
+int tgn_three_nn(int B, int N, int S, const float* xyz1, const float* xyz2, float* dist, int* idx, void* stream)
+{
+    using namespace tgn;
+    if (B <= 0 || N <= 0) return TGN_OK;
+    if (S < 3) { set_error("three_nn: needs at least 3 coarse points (S=%d)", S); return TGN_ERR_INVALID; }
+    if (B > 65535) { set_error("three_nn: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
+    dim3 grid((N + 127) / 128, B);
+    three_nn_kernel<128><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(N, S, xyz1, xyz2, dist, idx);
+    return check_launch("three_nn_kernel");
+}
+
+int tgn_three_interpolate(int B, int N, int S, int C, const float* points2, const float* dist, const int* idx, float* out,
+                          void* stream)
+{
+    using namespace tgn;
+    if (B <= 0 || N <= 0 || C <= 0) return TGN_OK;
+    if (B > 65535) { set_error("three_interpolate: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
+    const size_t total = static_cast<size_t>(N) * C;
+    const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 8 * static_cast<size_t>(sm_count())));
+    three_interpolate_kernel<<<dim3(blocks, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(N, S, C, points2, dist, idx, out);
+    return check_launch("three_interpolate_kernel");
+}
+
+}  // extern "C"

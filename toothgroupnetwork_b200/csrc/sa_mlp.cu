@@ -1,0 +1,226 @@
+// sa_mlp.cu -- fused set-abstraction body (gather -> shared MLP -> max over neighbours),
+// fp32 CUDA-core engine + the dispatcher of tgn_sa_group_mlp_max.
+//
+// The reference runs this as separate PyTorch ops: two advanced-index gathers, a subtract, a
+// cat, a permute, then per layer Conv2d(1x1) + BatchNorm2d + ReLU over a materialised
+// (B, C, K, S) tensor, then torch.max (external_libs/pointnet2_utils/pointnet2_utils.py:160-170,
+// 227-237, 276-294).  Here one CTA takes a tile of up to 128 grouped rows, builds the
+// [xyz_rel | feats] rows in shared memory straight from the index table, runs every layer out
+// of shared memory (ping-pong activation buffers, weights staged per layer) and reduces the K
+// rows of each group before anything is written: HBM sees the inputs once and (B, C_out, S) once.
+//
+// This engine is exact fp32 FMA arithmetic and handles any K and any widths <= 128; it is the
+// numerical reference for, and the fallback of, the tcgen05 engine in sa_mlp_tc.cu.
+#include <algorithm>
+
+#include "common.cuh"
+#include "sa_mlp.cuh"
+#include "tgn_b200.h"
+
+namespace tgn {
+namespace {
+
+constexpr int kRowsMax = 128;
+constexpr int kThreads = 256;
+
+// Build activation rows [xyz_rel | feats] (or [feats | xyz_rel]) for `rows` grouped rows.
+__device__ __forceinline__ void gather_rows_to_smem(const SaParams& p, int b, int s0, int row0_in_group, int rows,
+                                                    const int* jrow, float* act, int cs)
+{
+    const int cin = p.ch[0];
+    const float* xyz = p.xyz + 3 * static_cast<size_t>(b) * p.N;
+    const float* feats = p.feats ? p.feats + static_cast<size_t>(b) * p.N * p.D : nullptr;
+    for (int e = threadIdx.x; e < rows * cin; e += kThreads) {
+        const int r = e / cin, c = e - r * cin;
+        const int j = jrow[r];
+        const int s = s0 + (p.K <= kRowsMax ? r / p.K : 0);
+        const int xc = p.xyz_first ? c : c - p.D;          // channel inside the xyz block, if any
+        float v = 0.f;
+        if (j >= 0 && j < p.N) {
+            if (xc >= 0 && xc < 3)
+                v = __fsub_rn(__ldg(xyz + 3 * static_cast<size_t>(j) + xc),
+                              __ldg(p.new_xyz + 3 * (static_cast<size_t>(b) * p.S + s) + xc));
+            else
+                v = __ldg(feats + static_cast<size_t>(j) * p.D + (p.xyz_first ? c - 3 : c));
+        }
+        act[r * cs + c] = v;
+    }
+    (void)row0_in_group;
+}
+
+template <int CPW>   // output columns per warp (8 warps): 4 rows x CPW columns per thread
+__device__ __forceinline__ void dense_layer(const float* __restrict__ act_in, float* __restrict__ act_out, const float* wt,
+                                            const float* __restrict__ bias, int cin, int cout, int cout_pad, int cs)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = warp * CPW;
+    if (c0 >= cout) return;
+    float acc[4][CPW];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) acc[r][c] = 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+        float a[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = act_in[(lane + 32 * r) * cs + ci];
+#pragma unroll
+        for (int c4 = 0; c4 < CPW / 4; ++c4) {
+            const float4 w = *reinterpret_cast<const float4*>(wt + ci * cout_pad + c0 + 4 * c4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[r][4 * c4 + 0] = __fmaf_rn(a[r], w.x, acc[r][4 * c4 + 0]);
+                acc[r][4 * c4 + 1] = __fmaf_rn(a[r], w.y, acc[r][4 * c4 + 1]);
+                acc[r][4 * c4 + 2] = __fmaf_rn(a[r], w.z, acc[r][4 * c4 + 2]);
+                acc[r][4 * c4 + 3] = __fmaf_rn(a[r], w.w, acc[r][4 * c4 + 3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+        const int co = c0 + c;
+        if (co < cout) {
+            const float bv = __ldg(bias + co);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) act_out[(lane + 32 * r) * cs + co] = fmaxf(acc[r][c] + bv, 0.f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+sa_mlp_fp32_kernel(const SaParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int cs = p.cstride;
+    float* act0 = smem;
+    float* act1 = act0 + kRowsMax * cs;
+    float* wt = act1 + kRowsMax * cs;                          // [cin][cout_pad] of the current layer
+    int* jrow = reinterpret_cast<int*>(wt + p.wt_floats);
+
+    const int b = blockIdx.y;
+    int s0, rows, k0 = 0;
+    if (p.K <= kRowsMax) {
+        s0 = blockIdx.x * p.gpt;
+        rows = min(p.gpt, p.S - s0) * p.K;
+    } else {
+        s0 = blockIdx.x / p.chunks;
+        k0 = (blockIdx.x % p.chunks) * kRowsMax;
+        rows = min(kRowsMax, p.K - k0);
+    }
+    const int* gi = p.gidx + (static_cast<size_t>(b) * p.S + s0) * p.K + k0;
+    for (int r = threadIdx.x; r < kRowsMax; r += kThreads) jrow[r] = r < rows ? __ldg(gi + r) : -1;
+    __syncthreads();
+    gather_rows_to_smem(p, b, s0, k0, rows, jrow, act0, cs);
+    // rows past `rows` are never read back; zero them once so the FMAs stay finite
+    for (int e = threadIdx.x + rows * cs; e < kRowsMax * cs; e += kThreads) act0[e] = 0.f;
+
+    float* cur = act0;
+    float* nxt = act1;
+    for (int l = 0; l < p.L; ++l) {
+        const int cin = p.ch[l], cout = p.ch[l + 1];
+        const int cout_pad = (cout + 15) & ~15;
+        __syncthreads();                                        // previous layer done with wt / cur ready
+        for (int e = threadIdx.x; e < cin * cout_pad; e += kThreads) {
+            const int ci = e / cout_pad, co = e - ci * cout_pad;
+            wt[e] = co < cout ? __ldg(p.W[l] + static_cast<size_t>(co) * cin + ci) : 0.f;
+        }
+        __syncthreads();
+        const int cpw = (cout + 7) / 8;
+        if (cpw <= 4) dense_layer<4>(cur, nxt, wt, p.bias[l], cin, cout, cout_pad, cs);
+        else if (cpw <= 8) dense_layer<8>(cur, nxt, wt, p.bias[l], cin, cout, cout_pad, cs);
+        else dense_layer<16>(cur, nxt, wt, p.bias[l], cin, cout, cout_pad, cs);
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    __syncthreads();
+
+    // ---- max over the K rows of each group, channel-first store --------------------------------
+    const int cout = p.ch[p.L];
+    float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
+    if (p.K <= kRowsMax) {
+        const int groups = rows / p.K;
+        for (int e = threadIdx.x; e < groups * cout; e += kThreads) {
+            const int g = e / cout, co = e - g * cout;
+            float m = cur[(g * p.K) * cs + co];
+            for (int k = 1; k < p.K; ++k) m = fmaxf(m, cur[(g * p.K + k) * cs + co]);
+            ob[static_cast<size_t>(co) * p.S + s0 + g] = m;
+        }
+    } else {
+        for (int co = threadIdx.x; co < cout; co += kThreads) {
+            float m = cur[co];
+            for (int k = 1; k < rows; ++k) m = fmaxf(m, cur[k * cs + co]);
+            // post-ReLU values are >= 0, so integer order == float order and 0 is the identity
+            atomicMax(reinterpret_cast<int*>(ob + static_cast<size_t>(co) * p.S + s0), __float_as_int(m));
+        }
+    }
+}
+
+}  // namespace
+
+int sa_mlp_fp32_launch(SaParams p, cudaStream_t st)
+{
+    int cmax = 0, wmax = 0;
+    for (int l = 0; l <= p.L; ++l) cmax = std::max(cmax, p.ch[l]);
+    for (int l = 0; l < p.L; ++l) wmax = std::max(wmax, p.ch[l] * ((p.ch[l + 1] + 15) & ~15));
+    p.cstride = cmax | 1;                       // odd row stride: conflict-free column walks
+    p.wt_floats = (wmax + 3) & ~3;
+    const size_t smem = (2ull * kRowsMax * p.cstride + p.wt_floats) * sizeof(float) + kRowsMax * sizeof(int);
+    if (smem > 227 * 1024) { set_error("sa_group_mlp_max: %zu bytes of shared memory needed", smem); return TGN_ERR_INVALID; }
+    static size_t configured = 0;
+    if (smem > configured) {
+        const cudaError_t e = cudaFuncSetAttribute(sa_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
+        configured = smem;
+    }
+    dim3 grid;
+    if (p.K <= kRowsMax) {
+        p.gpt = kRowsMax / p.K;
+        p.chunks = 1;
+        grid = dim3((p.S + p.gpt - 1) / p.gpt, p.B);
+    } else {
+        p.gpt = 1;
+        p.chunks = (p.K + kRowsMax - 1) / kRowsMax;
+        grid = dim3(p.S * p.chunks, p.B);
+        // partial maxima are merged with atomicMax: clear this branch's slice of out first
+        const cudaError_t e = cudaMemset2DAsync(p.out + static_cast<size_t>(p.out_c_offset) * p.S,
+                                                static_cast<size_t>(p.out_c_total) * p.S * sizeof(float), 0,
+                                                static_cast<size_t>(p.ch[p.L]) * p.S * sizeof(float), p.B, st);
+        if (e != cudaSuccess) { set_error("cudaMemset2DAsync: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
+    }
+    sa_mlp_fp32_kernel<<<grid, kThreads, smem, st>>>(p);
+    return check_launch("sa_mlp_fp32_kernel");
+}
+
+}  // namespace tgn
+
+extern "C" int tgn_sa_group_mlp_max(int B, int N, int S, int K, int D, const float* xyz, const float* feats,
+                                    const float* new_xyz, const int* group_idx, int xyz_first, int n_layers,
+                                    const int* channels, const float* const* weights, const float* const* biases,
+                                    float* out, int out_c_total, int out_c_offset, int engine, void* stream)
+{
+    using namespace tgn;
+    if (B <= 0 || S <= 0) return TGN_OK;
+    if (N <= 0 || K <= 0) { set_error("sa_group_mlp_max: N and K must be positive"); return TGN_ERR_INVALID; }
+    if (B > 65535) { set_error("sa_group_mlp_max: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
+    if (n_layers < 1 || n_layers > kSaMaxLayers) { set_error("sa_group_mlp_max: 1..%d layers supported, got %d", kSaMaxLayers, n_layers); return TGN_ERR_INVALID; }
+    if (D < 0 || (D > 0 && !feats)) { set_error("sa_group_mlp_max: feats missing for D=%d", D); return TGN_ERR_INVALID; }
+    if (channels[0] != 3 + D) { set_error("sa_group_mlp_max: channels[0]=%d but 3+D=%d", channels[0], 3 + D); return TGN_ERR_INVALID; }
+    SaParams p{};
+    p.B = B; p.N = N; p.S = S; p.K = K; p.D = D;
+    p.xyz = xyz; p.feats = feats; p.new_xyz = new_xyz; p.gidx = group_idx;
+    p.xyz_first = xyz_first; p.L = n_layers;
+    for (int l = 0; l <= n_layers; ++l) {
+        p.ch[l] = channels[l];
+        if (channels[l] < 1 || channels[l] > kSaMaxWidth) {
+            set_error("sa_group_mlp_max: layer width %d outside [1,%d]", channels[l], kSaMaxWidth);
+            return TGN_ERR_INVALID;
+        }
+    }
+    for (int l = 0; l < n_layers; ++l) { p.W[l] = weights[l]; p.bias[l] = biases[l]; }
+    p.out = out; p.out_c_total = out_c_total; p.out_c_offset = out_c_offset;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (engine == 2 || (engine == 0 && sa_mlp_tc_supported(p))) {
+        if (!sa_mlp_tc_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
+        return sa_mlp_tc_launch(p, st);
+    }
+    return sa_mlp_fp32_launch(p, st);
+}

@@ -1,0 +1,31 @@
+// sa_mlp.cuh -- parameter block shared by the two engines of the fused set-abstraction body.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tgn {
+
+constexpr int kSaMaxLayers = 4;
+constexpr int kSaMaxWidth = 128;
+
+struct SaParams {
+    int B, N, S, K, D;
+    const float* xyz;        // (B,N,3)
+    const float* feats;      // (B,N,D) point-major, or nullptr
+    const float* new_xyz;    // (B,S,3)
+    const int* gidx;         // (B,S,K)
+    int xyz_first;           // 1: [xyz_rel, feats]  0: [feats, xyz_rel]
+    int L;
+    int ch[kSaMaxLayers + 1];
+    const float* W[kSaMaxLayers];      // (C_{l+1}, C_l) row-major, BatchNorm folded
+    const float* bias[kSaMaxLayers];
+    float* out;              // (B, out_c_total, S)
+    int out_c_total, out_c_offset;
+    // filled by the launchers
+    int cstride, wt_floats, gpt, chunks;
+};
+
+int sa_mlp_fp32_launch(SaParams p, cudaStream_t st);
+bool sa_mlp_tc_supported(const SaParams& p);
+int sa_mlp_tc_launch(SaParams p, cudaStream_t st);
+
+}  // namespace tgn

@@ -1,0 +1,321 @@
+// sa_mlp_tc.cu -- tcgen05 (5th-gen tensor core) engine of the fused set-abstraction body.
+//
+// Same contract as the fp32 engine in sa_mlp.cu, but the per-layer contraction
+//      D[128 rows, N] = A[128 rows, K] * W[N, K]^T
+// runs on the tensor cores with the accumulator in TENSOR MEMORY:
+//   * one CTA = 128 threads = 128 grouped rows (128/K groups); thread r owns row r end to end:
+//     it gathers its neighbour's [xyz_rel | feats] row, and after each layer reads ITS accumulator
+//     lane back with tcgen05.ld (32x32b: warp w owns TMEM lanes 32w..32w+31), applies
+//     bias + ReLU and writes the next layer's A operand -- the grouped tensor and the
+//     inter-layer activations never leave the SM;
+//   * operands live in shared memory in the canonical K-major, no-swizzle UMMA layout
+//     (8x16-byte core matrices; element (r,k) at (k/4)*LBO + r*16 + (k%4)*4 with SBO = 128 B), which a
+//     row-per-thread writer fills with conflict-free 16-byte stores;
+//   * fp32 fidelity: inputs are split a = a_hi + a_lo with a_hi the tf32 truncation, and each
+//     K-step issues three kind::tf32 MMAs (hi*hi + lo*hi + hi*lo) into the same accumulator
+//     ("3xTF32"), so the result carries ~2^-21 relative error instead of tf32's 2^-10 -- the
+//     reference's own default for these 1x1 convolutions is plain TF32;
+//   * one elected thread issues the MMAs and tcgen05.commit's an mbarrier the 128 threads wait on.
+// Weights are split and laid out once per CTA; CTAs are persistent over tiles.
+#include <algorithm>
+
+#include "common.cuh"
+#include "sa_mlp.cuh"
+#include "tgn_b200.h"
+
+namespace tgn {
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kThreads = 128;
+constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kChunkStrideA = kRows * 16;        // LBO of the A operand: one 16-byte K-chunk of all rows
+
+struct TcLayout {
+    int kpad[kSaMaxLayers];          // K of layer l, multiple of 8
+    int npad[kSaMaxLayers];          // N of layer l, multiple of 16
+    uint32_t w_hi[kSaMaxLayers], w_lo[kSaMaxLayers], bias[kSaMaxLayers];   // byte offsets in dynamic smem
+    uint32_t a_hi, a_lo;             // A operands; a_hi doubles as the fp32 staging area of the last layer
+    uint32_t misc;                   // tmem base (u32) + mbarrier (u64)
+    uint32_t total;
+    int tiles_per_cloud, gpt, stage_stride;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;                 // descriptor version for sm_100
+    return d;                        // layout type 0 (no swizzle), base offset 0
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(kRows >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// a = hi + lo with hi the tf32 truncation of a (exact split)
+__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(a) & 0xFFFFE000u;
+    lo = __float_as_uint(__fsub_rn(a, __uint_as_float(hi)));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + lay.misc);
+    const uint32_t bar = sbase + lay.misc + 8;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + lay.misc), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    // ---- weights: split into tf32 hi/lo, canonical K-major layout (LBO = npad*16, SBO = 128) -------
+    for (int l = 0; l < p.L; ++l) {
+        const int cin = p.ch[l], cout = p.ch[l + 1], kp = lay.kpad[l], np = lay.npad[l];
+        for (int e = tid; e < np * kp; e += kThreads) {
+            const int n = e / kp, k = e - n * kp;
+            const float w = (n < cout && k < cin) ? __ldg(p.W[l] + static_cast<size_t>(n) * cin + k) : 0.f;
+            uint32_t hi, lo;
+            split_tf32(w, hi, lo);
+            const uint32_t off = static_cast<uint32_t>(k >> 2) * (np * 16) + n * 16 + (k & 3) * 4;
+            *reinterpret_cast<uint32_t*>(smem + lay.w_hi[l] + off) = hi;
+            *reinterpret_cast<uint32_t*>(smem + lay.w_lo[l] + off) = lo;
+        }
+        float* bs = reinterpret_cast<float*>(smem + lay.bias[l]);
+        for (int n = tid; n < np; n += kThreads) bs[n] = n < cout ? __ldg(p.bias[l] + n) : 0.f;
+    }
+    proxy_fence_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    uint32_t phase = 0;
+
+    const int cin0 = p.ch[0];
+    const int total_tiles = lay.tiles_per_cloud * p.B;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / lay.tiles_per_cloud;
+        const int s0 = (tile - b * lay.tiles_per_cloud) * lay.gpt;
+        const int groups = min(lay.gpt, p.S - s0);
+        const int rows = groups * p.K;
+
+        // ---- layer-0 operand: this thread's grouped row --------------------------------------------
+        {
+            const int r = tid;
+            int j = -1, s = s0;
+            if (r < rows) {
+                s = s0 + r / p.K;
+                j = __ldg(p.gidx + (static_cast<size_t>(b) * p.S + s0) * p.K + r);
+                if (j < 0 || j >= p.N) j = -1;
+            }
+            const float* px = p.xyz + 3 * (static_cast<size_t>(b) * p.N + (j < 0 ? 0 : j));
+            const float* pc = p.new_xyz + 3 * (static_cast<size_t>(b) * p.S + s);
+            const float* pf = p.feats ? p.feats + (static_cast<size_t>(b) * p.N + (j < 0 ? 0 : j)) * p.D : nullptr;
+            for (int kc = 0; kc < lay.kpad[0] / 4; ++kc) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = 4 * kc + i;
+                    float v = 0.f;
+                    if (j >= 0 && c < cin0) {
+                        const int xc = p.xyz_first ? c : c - p.D;
+                        if (xc >= 0 && xc < 3) v = __fsub_rn(__ldg(px + xc), __ldg(pc + xc));
+                        else v = __ldg(pf + (p.xyz_first ? c - 3 : c));
+                    }
+                    split_tf32(v, hi[i], lo[i]);
+                }
+                const uint32_t off = kc * kChunkStrideA + r * 16;
+                st_shared_v4(sbase + lay.a_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(sbase + lay.a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+
+        for (int l = 0; l < p.L; ++l) {
+            const int kp = lay.kpad[l], np = lay.npad[l];
+            proxy_fence_async();           // this thread's operand stores -> visible to the tensor core
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = make_idesc_tf32(np);
+                const uint32_t lbo_b = static_cast<uint32_t>(np) * 16;
+                for (int ks = 0; ks < kp / 8; ++ks) {
+                    const uint64_t a_hi = make_smem_desc(sbase + lay.a_hi + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
+                    const uint64_t a_lo = make_smem_desc(sbase + lay.a_lo + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
+                    const uint64_t b_hi = make_smem_desc(sbase + lay.w_hi[l] + ks * 2 * lbo_b, lbo_b, 128);
+                    const uint64_t b_lo = make_smem_desc(sbase + lay.w_lo[l] + ks * 2 * lbo_b, lbo_b, 128);
+                    mma_tf32_ss(tmem_base, a_hi, b_hi, idesc, ks > 0);
+                    mma_tf32_ss(tmem_base, a_lo, b_hi, idesc, true);
+                    mma_tf32_ss(tmem_base, a_hi, b_lo, idesc, true);
+                }
+                mma_commit(bar);           // arrives on the mbarrier when the MMAs above have completed
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+
+            const float* bs = reinterpret_cast<const float*>(smem + lay.bias[l]);
+            const bool last = (l == p.L - 1);
+            float* stage = reinterpret_cast<float*>(smem + lay.a_hi);
+            for (int c0 = 0; c0 < np; c0 += 32) {
+                uint32_t v[32];
+                const bool full = np - c0 >= 32;             // np is a multiple of 16: a chunk is 32 or 16 wide
+                if (full) tmem_ld32(tmem_row + c0, v);
+                else tmem_ld16(tmem_row + c0, v);
+                if (!last) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (i < 16 || full) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                split_tf32(fmaxf(__uint_as_float(v[i + u]) + bs[c0 + i + u], 0.f), hi[u], lo[u]);
+                            const uint32_t off = static_cast<uint32_t>((c0 + i) >> 2) * kChunkStrideA + tid * 16;
+                            st_shared_v4(sbase + lay.a_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                            st_shared_v4(sbase + lay.a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < 16 || full)
+                            stage[tid * lay.stage_stride + c0 + i] = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f);
+                }
+            }
+            tc_fence_before();             // TMEM reads done before the next layer's MMAs overwrite D
+        }
+        __syncthreads();
+
+        // ---- max over the K rows of each group, channel-first store ---------------------------------
+        {
+            const int cout = p.ch[p.L];
+            const float* stage = reinterpret_cast<const float*>(smem + lay.a_hi);
+            float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
+            for (int e = tid; e < groups * cout; e += kThreads) {
+                const int g = e / cout, co = e - g * cout;
+                float m = stage[(g * p.K) * lay.stage_stride + co];
+                for (int k = 1; k < p.K; ++k) m = fmaxf(m, stage[(g * p.K + k) * lay.stage_stride + co]);
+                ob[static_cast<size_t>(co) * p.S + s0 + g] = m;
+            }
+        }
+        __syncthreads();                   // staging area becomes the next tile's A operand
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+bool make_layout(const SaParams& p, TcLayout& lay)
+{
+    if (p.K > kRows || p.K < 1) return false;
+    int kmax = 0, nlast = 0;
+    uint32_t off = 0;
+    auto take = [&off](uint32_t bytes, uint32_t align) {
+        off = (off + align - 1) / align * align;
+        const uint32_t o = off;
+        off += bytes;
+        return o;
+    };
+    for (int l = 0; l < p.L; ++l) {
+        lay.kpad[l] = l == 0 ? (p.ch[0] + 7) / 8 * 8 : lay.npad[l - 1];
+        lay.npad[l] = (p.ch[l + 1] + 15) / 16 * 16;
+        if (lay.npad[l] > 128 || lay.kpad[l] > 128) return false;
+        kmax = std::max(kmax, lay.kpad[l]);
+        nlast = lay.npad[l];
+    }
+    lay.stage_stride = nlast + 1;
+    const uint32_t a_bytes = static_cast<uint32_t>(kmax / 4) * kChunkStrideA;
+    const uint32_t stage_bytes = static_cast<uint32_t>(kRows) * lay.stage_stride * 4;
+    lay.a_hi = take(std::max(a_bytes, stage_bytes), 1024);
+    lay.a_lo = take(a_bytes, 1024);
+    for (int l = 0; l < p.L; ++l) {
+        const uint32_t wb = static_cast<uint32_t>(lay.npad[l]) * lay.kpad[l] * 4;
+        lay.w_hi[l] = take(wb, 128);
+        lay.w_lo[l] = take(wb, 128);
+        lay.bias[l] = take(lay.npad[l] * 4, 16);
+    }
+    lay.misc = take(16, 16);
+    lay.total = off;
+    lay.gpt = kRows / p.K;
+    lay.tiles_per_cloud = (p.S + lay.gpt - 1) / lay.gpt;
+    return lay.total <= 200 * 1024;
+}
+
+}  // namespace
+
+bool sa_mlp_tc_supported(const SaParams& p)
+{
+    TcLayout lay{};
+    return make_layout(p, lay);
+}
+
+int sa_mlp_tc_launch(SaParams p, cudaStream_t st)
+{
+    TcLayout lay{};
+    if (!make_layout(p, lay)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
+    static uint32_t configured = 0;
+    if (lay.total > configured) {
+        const cudaError_t e = cudaFuncSetAttribute(sa_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lay.total));
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
+        configured = lay.total;
+    }
+    const int per_sm = std::max(1, std::min<int>(4, static_cast<int>((220u * 1024u) / (lay.total + 1024u))));
+    const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
+    const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(sm_count()) * per_sm));
+    sa_mlp_tc_kernel<<<grid, kThreads, lay.total, st>>>(p, lay);
+    return check_launch("sa_mlp_tc_kernel");
+}
+
+}  // namespace tgn

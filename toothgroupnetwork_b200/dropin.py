@@ -1,0 +1,58 @@
+"""Make the reference's import paths resolve to this package.
+
+    import toothgroupnetwork_b200.dropin as dropin
+    dropin.install()
+    from models.modules import pointnet_pp        # reference code, unmodified
+
+After ``install()`` the modules the reference's callers import
+(``blocks.py:6``, ``heads.py:6``, ``basic_operators.py:4``, ``gen_utils.py:8``, ``pointnet_pp.py:3``,
+``tsg_centroid_module.py:3``, ``tsg_seg_module.py:3``, ``tsegnet.py:8``, ``tgn_loss.py:4``,
+``tsg_loss.py:2`` ...) are served from here:
+
+    external_libs.pointops.functions.pointops      -> toothgroupnetwork_b200.pointops
+    external_libs.pointnet2_utils.pointnet2_utils  -> toothgroupnetwork_b200.pointnet2_utils
+    pointops_cuda                                  -> toothgroupnetwork_b200.pointops_cuda
+
+Existing ``external_libs`` packages on ``sys.path`` (the reference checkout) keep serving every
+other submodule (``external_libs.scheduler`` ...): only the three names above are overridden.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+_TARGETS = {
+    "external_libs.pointops.functions.pointops": "toothgroupnetwork_b200.pointops",
+    "external_libs.pointnet2_utils.pointnet2_utils": "toothgroupnetwork_b200.pointnet2_utils",
+    "pointops_cuda": "toothgroupnetwork_b200.pointops_cuda",
+}
+
+
+def _ensure_package(name: str) -> types.ModuleType:
+    if name in sys.modules:
+        return sys.modules[name]
+    try:
+        return importlib.import_module(name)
+    except Exception:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = []          # namespace-like package
+        sys.modules[name] = pkg
+        if "." in name:
+            parent, _, child = name.rpartition(".")
+            setattr(_ensure_package(parent), child, pkg)
+        return pkg
+
+
+def install() -> None:
+    for alias, target in _TARGETS.items():
+        mod = importlib.import_module(target)
+        if "." in alias:
+            parent, _, child = alias.rpartition(".")
+            setattr(_ensure_package(parent), child, mod)
+        sys.modules[alias] = mod
+
+
+def uninstall() -> None:
+    for alias in _TARGETS:
+        sys.modules.pop(alias, None)

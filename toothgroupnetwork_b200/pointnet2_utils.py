@@ -1,0 +1,447 @@
+"""Operator / module API of ``external_libs/pointnet2_utils/pointnet2_utils.py`` on
+libtgn_b200.so.
+
+Same public names, signatures, tensor layouts ((B,C,N) channel-first in and out) and
+``state_dict`` keys (``mlp_convs.i``, ``mlp_bns.i``, ``conv_blocks.i.j``, ``bn_blocks.i.j``) as the
+reference, so ``models/modules/{pointnet_pp,tsg_centroid_module,tsg_seg_module}.py`` and the
+losses import it unchanged and checkpoints load.  What changes is underneath:
+
+* FPS, ball query, 3-NN, gathers and transposes are hand-written sm_100a kernels (the reference
+  runs ball query / 3-NN as dense torch ops with (S,N) matrices and full sorts);
+* in inference (``module.eval()`` and no autograd) a set-abstraction level is ONE fused kernel
+  per radius branch: gather -> [xyz_rel|feats] -> (conv1x1+BN+ReLU)* -> max over K, BatchNorm
+  folded into the conv weights, nothing materialised (tcgen05 3xTF32 engine, fp32 engine as
+  fallback);
+* when BatchNorm must use batch statistics (``module.training``) or gradients are needed, the
+  grouped tensor is built by the CUDA gather (with its scatter-add backward) and the 1x1
+  convolutions run through torch (cuBLAS/cuDNN) exactly as in the reference.
+
+There is no CPU path.  Reference line numbers below refer to that file.
+"""
+from __future__ import annotations
+
+import ctypes
+from time import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib as L
+from . import pointops
+
+SA_FUSED_MAX_WIDTH = 128
+SA_FUSED_MAX_LAYERS = 4
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TC = 0, 1, 2
+_sa_engine = ENGINE_AUTO
+
+
+def set_sa_engine(engine: int) -> None:
+    """Select the engine of the fused set-abstraction kernel (0 auto, 1 fp32 CUDA cores, 2 tcgen05)."""
+    global _sa_engine
+    _sa_engine = int(engine)
+
+
+def timeit(tag, t):
+    print("{}: {}s".format(tag, time() - t))
+    return time()
+
+
+def pc_normalize(pc):
+    """:12-18 (host-side numpy helper)."""
+    pc = pc - np.mean(pc, axis=0)
+    return pc / np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
+
+
+# ------------------------------------------------------------------------------------------ primitives
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(t)
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def transpose_last2(x: torch.Tensor) -> torch.Tensor:
+    """(B, R, C) -> (B, C, R) contiguous through the tiled transpose kernel."""
+    x = _f32c(x)
+    B, R, C = x.shape
+    out = torch.empty((B, C, R), dtype=torch.float32, device=x.device)
+    L.call("tgn_transpose_cn", B, R, C, L.ptr(x), L.ptr(out), L.stream_ptr())
+    return out
+
+
+class _Transpose(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return transpose_last2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return transpose_last2(g)
+
+
+def _transpose(x: torch.Tensor) -> torch.Tensor:
+    return _Transpose.apply(x) if x.requires_grad else transpose_last2(x)
+
+
+class _GatherRows(Function):
+    """points (B,N,C), idx (B,M) int32 -> (B,M,C); backward = scatter-add."""
+
+    @staticmethod
+    def forward(ctx, points, idx):
+        B, N, C = points.shape
+        M = idx.shape[1]
+        out = torch.empty((B, M, C), dtype=torch.float32, device=points.device)
+        L.call("tgn_gather_rows", B, N, M, C, L.ptr(points), L.ptr(idx), L.ptr(out), L.stream_ptr())
+        ctx.shape = (B, N, C)
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        B, N, C = ctx.shape
+        M = idx.shape[1]
+        flat = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N).view(B, 1)).contiguous()
+        gi = torch.zeros((B * N, C), dtype=torch.float32, device=g.device)
+        g = g.contiguous()
+        L.call("tgn_grouping_backward", B * M, 1, C, L.ptr(g), L.ptr(flat), L.ptr(gi), L.stream_ptr())
+        return gi.view(B, N, C), None
+
+
+def square_distance(src, dst):
+    """:20-41.  (B,N,C),(B,M,C) -> (B,N,M) in the expanded form -2ab + |a|^2 + |b|^2.
+    Dense library ops (this is the reference's own formulation; it is differentiable and only
+    the losses call it on a handful of centroids).  The neighbourhood searches below never
+    materialise this matrix."""
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    dist += torch.sum(src ** 2, -1).view(B, N, 1)
+    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
+    return dist
+
+
+def index_points(points, idx):
+    """:44-61.  points (B,N,C), idx (B,S) or (B,S,K) integer -> (B,S[,K],C)."""
+    pts = _f32c(points)
+    B = pts.shape[0]
+    flat = idx.reshape(B, -1).to(torch.int32).contiguous()
+    out = _GatherRows.apply(pts, flat)
+    return out.view(*idx.shape, pts.shape[-1])
+
+
+def _take_rows(packed: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """packed (n,c) float32, rows (m,) int32 -> (m,c) through the gather kernel."""
+    m, c = rows.shape[0], packed.shape[1]
+    out = torch.empty((m, c), dtype=torch.float32, device=packed.device)
+    L.call("tgn_grouping_forward", m, 1, c, L.ptr(packed), L.ptr(rows), L.ptr(out), L.stream_ptr())
+    return out
+
+
+def _fps_batched(xyz_t: torch.Tensor, npoint: int, mode: int = 0) -> torch.Tensor:
+    """xyz_t (B,N,3) contiguous -> GLOBAL int32 row ids (B*npoint,) of the packed (B*N,3) view."""
+    B, N, _ = xyz_t.shape
+    dev = xyz_t.device
+    offset = torch.arange(1, B + 1, device=dev, dtype=torch.int32) * N
+    new_offset = torch.arange(1, B + 1, device=dev, dtype=torch.int32) * npoint
+    return pointops.fps_packed(xyz_t.view(-1, 3), offset, new_offset, N, B * npoint, mode)
+
+
+def farthest_point_sample(xyz, npoint):
+    """:64-98.  xyz (B,N,3) -> per-cloud-local indices (B,npoint) int64; first sample = point 0."""
+    xyz_t = _f32c(xyz)
+    B, N, _ = xyz_t.shape
+    gidx = _fps_batched(xyz_t, int(npoint)).view(B, npoint).long()
+    return gidx - (torch.arange(B, device=xyz_t.device, dtype=torch.long) * N).view(B, 1)
+
+
+def farthest_point_sample_np(xyz, npoint):
+    """:103-118 samples a numpy cloud with a RANDOM start on whatever device the array lands on;
+    the reference never calls it.  Here: same contract (numpy in, numpy out) on the GPU kernel
+    with the deterministic start the live path uses."""
+    t = torch.from_numpy(np.asarray(xyz, dtype=np.float32)).cuda()
+    return farthest_point_sample(t, npoint).cpu().numpy()
+
+
+def _radius_sq_f32(radius: float) -> float:
+    """``sqrdists > radius ** 2`` compares against float32(radius**2) (:136; torch casts the
+    python scalar to the tensor dtype)."""
+    return float(np.float32(float(radius) ** 2))
+
+
+def _ball_query(radius, nsample, xyz_t, new_xyz_t, idx64: bool) -> torch.Tensor:
+    B, N, _ = xyz_t.shape
+    S = new_xyz_t.shape[1]
+    out = torch.empty((B, S, nsample), dtype=torch.int64 if idx64 else torch.int32, device=xyz_t.device)
+    L.call("tgn_ball_query", B, N, S, ctypes.c_float(_radius_sq_f32(radius)), int(nsample), L.ptr(xyz_t), L.ptr(new_xyz_t),
+           L.ptr(out), 1 if idx64 else 0, L.stream_ptr())
+    return out
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """:120-144.  xyz (B,N,3), new_xyz (B,S,3) -> (B,S,nsample) int64: first nsample indices in
+    ascending order inside the ball, padded with the first; N everywhere for an empty ball."""
+    return _ball_query(radius, nsample, _f32c(xyz), _f32c(new_xyz), True)
+
+
+def three_nn(xyz1, xyz2):
+    """Top-3 of square_distance(xyz1, xyz2) (:333-335) without the matrix or the sort:
+    (B,N,3),(B,S,3) -> dist (B,N,3) ascending, idx (B,N,3) int32."""
+    x1, x2 = _f32c(xyz1), _f32c(xyz2)
+    B, N, _ = x1.shape
+    S = x2.shape[1]
+    dist = torch.empty((B, N, 3), dtype=torch.float32, device=x1.device)
+    idx = torch.empty((B, N, 3), dtype=torch.int32, device=x1.device)
+    L.call("tgn_three_nn", B, N, S, L.ptr(x1), L.ptr(x2), L.ptr(dist), L.ptr(idx), L.stream_ptr())
+    return dist, idx
+
+
+def three_interpolate(points2, dist, idx):
+    """Inverse squared-distance interpolation (:337-340): points2 (B,S,C) -> (B,N,C).
+    Differentiable wrt points2."""
+    p2 = _f32c(points2)
+    B, S, C = p2.shape
+    N = idx.shape[1]
+    if not (p2.requires_grad and torch.is_grad_enabled()):
+        out = torch.empty((B, N, C), dtype=torch.float32, device=p2.device)
+        L.call("tgn_three_interpolate", B, N, S, C, L.ptr(p2), L.ptr(dist), L.ptr(idx), L.ptr(out), L.stream_ptr())
+        return out
+    rec = 1.0 / (dist + 1e-8)
+    w = (rec / torch.sum(rec, dim=2, keepdim=True)).reshape(B * N, 3).contiguous()
+    flat = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * S).view(B, 1, 1)).reshape(B * N, 3).contiguous()
+    return pointops._WeightedGather.apply(p2.reshape(B * S, C), flat, w).view(B, N, C)
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+    """:147-175.  xyz (B,N,3), points (B,N,D) -> new_xyz (B,S,3), new_points (B,S,K,3+D) with
+    channel order [xyz_rel, feats]."""
+    B, N, C = xyz.shape
+    fps_idx = farthest_point_sample(xyz, npoint)
+    new_xyz = index_points(xyz, fps_idx)
+    idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    grouped_xyz = index_points(xyz, idx)
+    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, npoint, 1, C)
+    if points is not None:
+        new_points = torch.cat([grouped_xyz_norm, index_points(points, idx)], dim=-1)
+    else:
+        new_points = grouped_xyz_norm
+    if returnfps:
+        return new_xyz, new_points, grouped_xyz, fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """:178-195.  One group holding the whole cloud; new_xyz is the origin."""
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device, dtype=xyz.dtype)
+    grouped_xyz = xyz.view(B, 1, N, C)
+    if points is not None:
+        return new_xyz, torch.cat([grouped_xyz, points.view(B, 1, N, -1)], dim=-1)
+    return new_xyz, grouped_xyz
+
+
+# ------------------------------------------------------------------------------------------ fused SA body
+class _FoldedMlp:
+    """conv1x1 + eval-mode BatchNorm folded to (W', b') per layer, cached until a parameter or
+    running statistic changes (tensor ``_version`` counters)."""
+
+    def __init__(self):
+        self.key = None
+        self.weights: List[torch.Tensor] = []
+        self.biases: List[torch.Tensor] = []
+        self.channels: List[int] = []
+        self.w_ptrs = None
+        self.b_ptrs = None
+
+    def update(self, convs, bns) -> "_FoldedMlp":
+        key = tuple((c.weight._version, c.weight.data_ptr(), None if c.bias is None else c.bias._version,
+                     b.weight._version, b.bias._version, b.running_mean._version, b.running_var._version, b.running_mean.data_ptr())
+                    for c, b in zip(convs, bns))
+        if key == self.key:
+            return self
+        self.weights, self.biases, self.channels = [], [], []
+        with torch.no_grad():
+            for c, b in zip(convs, bns):
+                w = c.weight.reshape(c.weight.shape[0], -1).float()
+                cb = c.bias.float() if c.bias is not None else torch.zeros(w.shape[0], device=w.device)
+                scale = b.weight.float() / torch.sqrt(b.running_var.float() + b.eps)
+                self.weights.append((w * scale[:, None]).contiguous())
+                self.biases.append(((cb - b.running_mean.float()) * scale + b.bias.float()).contiguous())
+                if not self.channels:
+                    self.channels.append(w.shape[1])
+                self.channels.append(w.shape[0])
+        n = len(self.weights)
+        self.w_ptrs = (ctypes.c_void_p * n)(*[w.data_ptr() for w in self.weights])
+        self.b_ptrs = (ctypes.c_void_p * n)(*[b.data_ptr() for b in self.biases])
+        self.key = key
+        return self
+
+
+def fused_supported(channels: Sequence[int]) -> bool:
+    return 1 <= len(channels) - 1 <= SA_FUSED_MAX_LAYERS and max(channels) <= SA_FUSED_MAX_WIDTH
+
+
+def sa_group_mlp_max(xyz_t, feats_t, new_xyz_t, group_idx, xyz_first: bool, folded: _FoldedMlp, out, c_offset: int,
+                     engine: Optional[int] = None) -> None:
+    """Launch the fused gather -> MLP -> max kernel for one radius branch, writing channels
+    [c_offset, c_offset + C_last) of ``out`` (B, C_total, S)."""
+    B, N, _ = xyz_t.shape
+    S, K = group_idx.shape[1], group_idx.shape[2]
+    D = 0 if feats_t is None else feats_t.shape[2]
+    ch = (ctypes.c_int * len(folded.channels))(*folded.channels)
+    L.call("tgn_sa_group_mlp_max", B, N, S, K, D, L.ptr(xyz_t), L.ptr(feats_t), L.ptr(new_xyz_t), L.ptr(group_idx),
+           1 if xyz_first else 0, len(folded.weights), ctypes.cast(ch, ctypes.c_void_p), ctypes.cast(folded.w_ptrs, ctypes.c_void_p),
+           ctypes.cast(folded.b_ptrs, ctypes.c_void_p), L.ptr(out), out.shape[1], int(c_offset),
+           _sa_engine if engine is None else int(engine), L.stream_ptr())
+
+
+def _wants_grad(module: nn.Module, *tensors) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def _mlp_unfused(grouped: torch.Tensor, convs, bns) -> torch.Tensor:
+    """grouped (B,S,K,C) -> (B,C_out,S): the reference's permute + conv/BN/ReLU + max (:227-237)."""
+    h = grouped.permute(0, 3, 2, 1)
+    for conv, bn in zip(convs, bns):
+        h = F.relu(bn(conv(h)))
+    return torch.max(h, 2)[0]
+
+
+class PointNetSetAbstraction(nn.Module):
+    """:198-239.  Single-scale set abstraction; group channel order [xyz_rel, feats]."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for width in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, width, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(width))
+            last = width
+        self._folded = _FoldedMlp()
+
+    def _fusable(self, xyz, points) -> bool:
+        chans = [self.mlp_convs[0].in_channels] + [c.out_channels for c in self.mlp_convs]
+        return (not self.training) and fused_supported(chans) and not _wants_grad(self, xyz, points)
+
+    def forward(self, xyz, points):
+        """xyz (B,3,N), points (B,D,N) or None -> new_xyz (B,3,S), new_points (B,C_out,S)."""
+        L.require_cuda(xyz, points)
+        xyz_t = _transpose(xyz)                                   # (B,N,3)
+        feats_t = None if points is None else _transpose(points)  # (B,N,D)
+        B, N, _ = xyz_t.shape
+        if self._fusable(xyz, points):
+            folded = self._folded.update(self.mlp_convs, self.mlp_bns)
+            if self.group_all:
+                S, K = 1, N
+                new_xyz_t = torch.zeros((B, 1, 3), dtype=torch.float32, device=xyz_t.device)
+                gidx = torch.arange(N, device=xyz_t.device, dtype=torch.int32).view(1, 1, N).expand(B, 1, N).contiguous()
+            else:
+                S, K = self.npoint, self.nsample
+                fps = _fps_batched(xyz_t, S)
+                new_xyz_t = _take_rows(xyz_t.view(-1, 3), fps).view(B, S, 3)
+                gidx = _ball_query(self.radius, K, xyz_t, new_xyz_t, False)
+            out = torch.empty((B, folded.channels[-1], S), dtype=torch.float32, device=xyz_t.device)
+            sa_group_mlp_max(xyz_t, feats_t, new_xyz_t, gidx, True, folded, out, 0)
+            return transpose_last2(new_xyz_t), out
+        if self.group_all:
+            new_xyz_t, grouped = sample_and_group_all(xyz_t, feats_t)
+        else:
+            new_xyz_t, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_t, feats_t)
+        return new_xyz_t.permute(0, 2, 1), _mlp_unfused(grouped, self.mlp_convs, self.mlp_bns)
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """:242-299.  Multi-scale grouping: one FPS, per radius a ball query + MLP + max, branches
+    concatenated on the channel axis; group channel order [feats, xyz_rel] (:285)."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for widths in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            last = in_channel + 3
+            for width in widths:
+                convs.append(nn.Conv2d(last, width, 1))
+                bns.append(nn.BatchNorm2d(width))
+                last = width
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self._folded = [_FoldedMlp() for _ in mlp_list]
+
+    def _fusable(self, xyz, points) -> bool:
+        if self.training or _wants_grad(self, xyz, points):
+            return False
+        return all(fused_supported([convs[0].in_channels] + [c.out_channels for c in convs]) for convs in self.conv_blocks)
+
+    def forward(self, xyz, points):
+        L.require_cuda(xyz, points)
+        xyz_t = _transpose(xyz)
+        feats_t = None if points is None else _transpose(points)
+        B, N, _ = xyz_t.shape
+        S = self.npoint
+        if self._fusable(xyz, points):
+            fps = _fps_batched(xyz_t, S)
+            new_xyz_t = _take_rows(xyz_t.view(-1, 3), fps).view(B, S, 3)
+            folded = [f.update(c, b) for f, c, b in zip(self._folded, self.conv_blocks, self.bn_blocks)]
+            out = torch.empty((B, sum(f.channels[-1] for f in folded), S), dtype=torch.float32, device=xyz_t.device)
+            c_off = 0
+            for radius, K, f in zip(self.radius_list, self.nsample_list, folded):
+                gidx = _ball_query(radius, K, xyz_t, new_xyz_t, False)
+                sa_group_mlp_max(xyz_t, feats_t, new_xyz_t, gidx, False, f, out, c_off)
+                c_off += f.channels[-1]
+            return transpose_last2(new_xyz_t), out
+        new_xyz_t = index_points(xyz_t, farthest_point_sample(xyz_t, S))
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            K = self.nsample_list[i]
+            gidx = query_ball_point(radius, K, xyz_t, new_xyz_t)
+            grouped = index_points(xyz_t, gidx) - new_xyz_t.view(B, S, 1, 3)
+            if feats_t is not None:
+                grouped = torch.cat([index_points(feats_t, gidx), grouped], dim=-1)
+            outs.append(_mlp_unfused(grouped, self.conv_blocks[i], self.bn_blocks[i]))
+        return new_xyz_t.permute(0, 2, 1), torch.cat(outs, dim=1)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """:302-352.  3-NN inverse squared-distance interpolation + skip concat + conv1x1/BN/ReLU."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for width in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, width, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(width))
+            last = width
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 (B,3,N) fine, xyz2 (B,3,S) coarse, points1 (B,D1,N) or None, points2 (B,D2,S)
+        -> (B,D',N)."""
+        L.require_cuda(xyz1, xyz2, points1, points2)
+        x1, x2 = _transpose(xyz1), _transpose(xyz2)
+        p2 = _transpose(points2)                                   # (B,S,D2)
+        B, N, _ = x1.shape
+        S = x2.shape[1]
+        if S == 1:
+            interp = p2.repeat(1, N, 1)
+        else:
+            dist, idx = three_nn(x1, x2)
+            interp = three_interpolate(p2, dist, idx)             # (B,N,D2)
+        h = _transpose(interp)                                     # (B,D2,N)
+        if points1 is not None:
+            h = torch.cat([points1, h], dim=1)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            h = F.relu(bn(conv(h)))
+        return h
