@@ -131,20 +131,11 @@ def cpu_reference_step(feats: torch.Tensor, sa_cpu_layers, threads: int):
     torch-loop FPS with start 0 (pointnet2_utils.py:103-118), query_ball_point (:120-144), gather,
     conv1x1+BN+ReLU x3, max (:227-237).  Clouds are spread over ``threads`` host threads for the
     sampling / search, the MLP runs with torch's intra-op threads."""
-    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
     xyz = feats[:, :3].permute(0, 2, 1).contiguous().numpy()
-
-    def one(b):
-        fps = oracle.fps_torchloop(xyz[b], NPOINT, 0)
-        new = xyz[b][fps]
-        gi = oracle.query_ball_point(RADIUS, NSAMPLE, xyz[b][None], new[None])[0]
-        return fps, new, gi
-
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        res = list(ex.map(one, range(feats.shape[0])))
-    new_xyz = torch.from_numpy(np.stack([r[1] for r in res]))
-    gidx = torch.from_numpy(np.stack([r[2] for r in res]))
+    _, new_np, gi_np = oracle.sa_sample_and_search_batch(xyz, NPOINT, RADIUS, NSAMPLE)   # one cloud per OpenMP thread
+    new_xyz = torch.from_numpy(new_np)
+    gidx = torch.from_numpy(gi_np)
     pts = feats.permute(0, 2, 1)
     xyz_t = torch.from_numpy(xyz)
     grouped = torch.cat([oracle.index_points(xyz_t, gidx) - new_xyz.unsqueeze(2), oracle.index_points(pts, gidx)], -1)
@@ -188,6 +179,8 @@ def main():
     ap.add_argument("--clouds", type=int, default=296, help="clouds per GPU per step")
     ap.add_argument("--cpu-clouds", type=int, default=0, help="clouds in the CPU sample (default: host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fps-mode", type=int, default=0, help="0 auto; 100*G+CS forces an FPS kernel shape (experiments)")
+    ap.add_argument("--sa-engine", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -224,6 +217,7 @@ def main():
     from toothgroupnetwork_b200 import pointnet2_utils as pn2
 
     sa = build_module(device)
+    pn2.set_sa_engine(args.sa_engine)
     B = args.clouds
     host_feats = make_clouds(rank, B).pin_memory()
     feats = host_feats.to(device)
@@ -236,7 +230,7 @@ def main():
         xyz_t = pn2.transpose_last2(xyz)
         feats_t = pn2.transpose_last2(feats)
         if events: events[0].record()
-        fps = pn2._fps_batched(xyz_t, NPOINT)
+        fps = pn2._fps_batched(xyz_t, NPOINT, args.fps_mode)
         if events: events[1].record()
         new_xyz_t = pn2._take_rows(xyz_t.view(-1, 3), fps).view(B, NPOINT, 3)
         gidx = pn2._ball_query(RADIUS, NSAMPLE, xyz_t, new_xyz_t, False)

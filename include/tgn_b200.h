@@ -76,8 +76,10 @@ int tgn_launch_count(void);                /* kernels launched by this library i
 
 /* FPS.  Same contract as furthestsampling_cuda_launcher; tmp may be NULL (running minima start
  * at 1e10 and are not written back) when the cloud fits the register-resident kernel.
- * `mode`: 0 = choose by b and n (throughput when b is large, latency when small),
- *         otherwise force a cluster size (1,2,4,8) or the streaming kernel (-1). */
+ * `mode`: 0 = choose by b and n (two clouds software-pipelined per cluster when the batch can
+ *         fill the machine, one cloud on a wide cluster when only a few are in flight),
+ *         -1 = streaming kernel, otherwise 100*G + CS forces a cluster of CS CTAs (1,2,4,8) with
+ *         G clouds in flight (1 or 2; G omitted = 1). */
 int tgn_furthestsampling(int b, int n_max, const float *xyz, const int *offset, const int *new_offset,
                          float *tmp, int *idx, int mode, void *stream);
 

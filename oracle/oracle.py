@@ -368,3 +368,16 @@ def feature_propagation(xyz1, xyz2, points1, points2, layers: Sequence[MlpParams
     for p in layers:
         h = _conv_bn_relu(h, p.to(dtype), train_bn)
     return h
+
+
+def sa_sample_and_search_batch(xyz, npoint, radius, nsample):
+    """FPS loop (start 0) + centre gather + ball query for a batch (B,N,3), one cloud per OpenMP
+    thread -- the CPU baseline of bench.py.  -> fps (B,S) int64, new_xyz (B,S,3), group_idx (B,S,K)."""
+    xyz = _f(xyz)
+    B, N, _ = xyz.shape
+    fps = np.empty((B, npoint), np.int64)
+    new_xyz = np.empty((B, npoint, 3), np.float32)
+    gidx = np.empty((B, npoint, nsample), np.int64)
+    lib().oracle_sa_sample_and_search_batch(B, N, int(npoint), ctypes.c_float(float(radius_sq_f32(radius))), int(nsample),
+                                            _p(xyz, _f32p), _p(fps, _i64p), _p(new_xyz, _f32p), _p(gidx, _i64p))
+    return fps, new_xyz, gidx

@@ -361,3 +361,23 @@ void oracle_fps_torchloop(int n, int npoint, int start, const float *xyz, float 
         far = besti;
     }
 }
+
+/* Sampling + neighbour search of one set-abstraction level for a batch of clouds, one cloud per
+ * OpenMP thread: the reference's CPU-capable FPS loop (pointnet2_utils.py:103-118, start 0),
+ * the gather of the sampled centres (:157) and query_ball_point (:120-144).  This is the host
+ * baseline bench.py times; the inner routines run serially inside each thread. */
+void oracle_sa_sample_and_search_batch(int B, int n, int npoint, float r2, int nsample, const float *xyz,
+                                       int64_t *fps, float *new_xyz, int64_t *group_idx)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < B; ++b) {
+        const float *cx = xyz + (size_t)b * n * 3;
+        int64_t *cf = fps + (size_t)b * npoint;
+        float *cn = new_xyz + (size_t)b * npoint * 3;
+        float *dist = (float *)malloc(sizeof(float) * (size_t)n);
+        oracle_fps_torchloop(n, npoint, 0, cx, dist, cf);
+        free(dist);
+        for (int s = 0; s < npoint; ++s) memcpy(cn + 3 * (size_t)s, cx + 3 * (size_t)cf[s], 3 * sizeof(float));
+        oracle_query_ball_point(n, npoint, r2, nsample, cx, cn, group_idx + (size_t)b * npoint * nsample);
+    }
+}

@@ -47,7 +47,7 @@ def _pack(cl, ms):
 
 
 @pytest.mark.parametrize("name,build,ms", FPS_CASES, ids=[c[0] for c in FPS_CASES])
-@pytest.mark.parametrize("mode", [0, 1, 2, 4, 8, -1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 4, 8, 201, 202, 204, 208, -1])   # 100*G + CS, see tgn_furthestsampling
 def test_fps_matches_oracle(name, build, ms, mode):
     cl = build()
     xyz, offset, new_offset = _pack(cl, ms)
@@ -56,7 +56,7 @@ def test_fps_matches_oracle(name, build, ms, mode):
     try:
         got = pointops.fps_packed(xyz.cuda(), i32(offset), i32(new_offset), n_max, int(new_offset[-1]), mode)
     except L.TgnError as e:
-        if mode > 0 and "resident" in str(e):
+        if mode > 0 and "no resident kernel of shape" in str(e):
             pytest.skip("cluster size not applicable to this cloud size")
         raise
     torch.cuda.synchronize()

@@ -100,6 +100,11 @@ __device__ __forceinline__ void st_async_v4(uint32_t dst, uint32_t a, uint32_t b
                  "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void st_async_v2(uint32_t dst, uint32_t a, uint32_t b, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst), "r"(a),
+                 "r"(b), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void st_async_b32(uint32_t dst, uint32_t a, uint32_t bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst), "r"(a), "r"(bar)
                  : "memory");

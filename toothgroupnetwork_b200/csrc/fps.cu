@@ -4,22 +4,28 @@
 // cloud re-streaming xyz+tmp from L2 every iteration, 11 block barriers per iteration).
 //
 // Design (DESIGN.md "FPS"):
-//  * A cloud is owned by a thread-block CLUSTER of CS CTAs.  Every point (x,y,z and its running
-//    minimum t) lives in REGISTERS for the whole kernel: thread u holds SLOTS points, packed two
-//    per 64-bit register so the distance update runs on FADD2/FMUL2/FFMA2.  HBM is touched once
-//    to load the cloud and once per sample to write idx.
-//  * Per iteration each WARP reduces its maximum with two CREDUX ops, the winning lane finds its
-//    slot, and publishes one candidate (t, j, x, y, z) straight into the mailbox of every CTA of
-//    the cluster with st.async, which also completes bytes on that CTA's mbarrier.  There is no
-//    __syncthreads in the loop: a warp continues as soon as the mailbox phase completes.
+//  * A thread-block CLUSTER of CS CTAs owns G clouds at a time.  Every point (x,y,z and its
+//    running minimum t) lives in REGISTERS for the whole kernel: thread u holds SLOTS points of
+//    each cloud, packed two per 64-bit register so the distance update runs on
+//    FADD2/FMUL2/FFMA2.  HBM is touched once to load the clouds and once per sample for idx.
+//  * The argmax is tracked inside the update loop on the ALU pipe (FSETP/FMNMX/SEL run beside the
+//    FP32 pipe, which is the bottleneck: 6 lane-ops per point-update), so no thread ever
+//    re-scans its registers.
+//  * Reduction is two-level and barrier-free: each warp reduces with two CREDUX ops and drops
+//    one candidate in shared memory + arrives on a CTA-local mbarrier; one publisher warp per
+//    cloud picks the CTA's candidate and sends (t, key, x, y, z, j) to the mailbox of every CTA of
+//    the cluster with st.async, which also completes bytes on that CTA's mbarrier.
+//  * G > 1 software-pipelines independent clouds through the same cluster: the candidates of
+//    cloud g travel while the SM updates cloud g+1, hiding the DSMEM/mbarrier round trip that
+//    dominates a single serial FPS chain.
 //  * Bit-exact tie-break.  The reference picks, among equal maxima, the point with the smallest
 //    (bitrev(j mod BS), j div BS) where BS is ITS block size (cuda_utils.h:11-14) and j the
 //    cloud-local index: thread tid scans j = tid, tid+BS, .. with a strict '>' (first maximum
 //    wins) and the shared-memory tree lets the lower entry win ties, which orders threads by the
 //    bit-reversed tid (sampling_cuda_kernel.cu:5-10,49-59,64-123).  Here thread u owns residue
-//    r = u mod BS and the contiguous slot range [q*SLOTS, (q+1)*SLOTS) with q = u div BS, so the
-//    order is (bitrev(r), q, slot) and a thread-level priority known without scanning suffices
-//    to elect the one lane that has to look at its slots.
+//    r = u mod BS and the contiguous slot range [q*SLOTS, (q+1)*SLOTS) with q = u div BS; its own
+//    scan is the same strict '>' in slot order, threads are ordered by (bitrev(r), q), and
+//    candidates by the point key (bitrev(j mod BS), j div BS).
 //  * Distance arithmetic is the reference's SASS sequence: t = dy*dy; t = fma(dx,dx,t);
 //    d = fma(dz,dz,t); min; all IEEE-rn, so indices are bit-identical.
 #include <algorithm>
@@ -32,8 +38,8 @@
 namespace tgn {
 namespace {
 
-constexpr int kCandWords = 8;      // one mailbox entry = 32 bytes (20 used)
-constexpr int kCandBytes = 20;     // bytes completed on the mbarrier per candidate
+constexpr int kCandWords = 8;      // one mailbox entry = 32 bytes (24 used)
+constexpr int kCandBytes = 24;     // bytes completed on the mbarrier per candidate
 
 __device__ __forceinline__ int bitrev_low(int v, int bits) {
     return bits ? static_cast<int>(__brev(static_cast<unsigned>(v)) >> (32 - bits)) : 0;
@@ -43,41 +49,57 @@ __device__ __forceinline__ int point_key(int j, int bs_log2) {
     return (bitrev_low(j & ((1 << bs_log2) - 1), bs_log2) << 21) | (j >> bs_log2);
 }
 
-template <int T, int SLOTS, int CS>
+template <int T, int SLOTS, int CS, int G>
 __global__ void __launch_bounds__(T, 1)
 fps_resident_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
-                    const int* __restrict__ new_offset, float* tmp, int* __restrict__ idx, int bs_log2)
+                    const int* __restrict__ new_offset, float* tmp, int* __restrict__ idx, int b, int bs_log2)
 {
     static_assert(SLOTS % 2 == 0, "slots are processed in packed pairs");
     constexpr int NW = T / 32;
-    constexpr int NCAND = CS * NW;
     constexpr int PAIRS = SLOTS / 2;
-    constexpr int NG = (PAIRS % 4 == 0) ? 4 : ((PAIRS % 2 == 0) ? 2 : 1);   // max accumulators
-    constexpr int PPG = PAIRS / NG;
     constexpr unsigned FULL = 0xffffffffu;
 
-    __shared__ __align__(16) uint32_t mailbox[2][NCAND * kCandWords];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(16) uint32_t mailbox[G][2][CS * kCandWords];   // one candidate per CTA of the cluster
+    __shared__ __align__(16) uint32_t wslot[G][2][NW * 4];              // one candidate per warp of this CTA
+    __shared__ __align__(8) uint64_t mbars[G][2];                       // mailbox full (cluster scope)
+    __shared__ __align__(8) uint64_t lbars[G][2];                       // warp candidates full (CTA scope)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
-    const int cloud = blockIdx.x / CS;
-    const int start_n = cloud ? offset[cloud - 1] : 0;
-    const int n = offset[cloud] - start_n;
-    const int start_m = cloud ? new_offset[cloud - 1] : 0;
-    const int m = new_offset[cloud] - start_m;
-    if (m <= 0 || n <= 0) return;                       // uniform across the cluster
-    if (rank == 0 && tid == 0) idx[start_m] = start_n;  // sampling_cuda_kernel.cu:39
-    if (m == 1) return;
+    const int cluster = blockIdx.x / CS;
 
-    const uint32_t bar_base = smem_u32(&bars[0]);   // bars[p] lives at bar_base + 8*p
+    int start_n[G], n[G], start_m[G], m[G];
+    int mmax = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int cloud = cluster * G + g;
+        start_n[g] = 0; n[g] = 0; start_m[g] = 0; m[g] = 0;
+        if (cloud < b) {
+            start_n[g] = cloud ? __ldg(offset + cloud - 1) : 0;
+            n[g] = __ldg(offset + cloud) - start_n[g];
+            start_m[g] = cloud ? __ldg(new_offset + cloud - 1) : 0;
+            m[g] = __ldg(new_offset + cloud) - start_m[g];
+            if (n[g] <= 0) m[g] = 0;
+            if (m[g] > 0 && rank == 0 && tid == 0) idx[start_m[g]] = start_n[g];   // sampling_cuda_kernel.cu:39
+        }
+        mmax = max(mmax, m[g]);
+    }
+    if (mmax <= 1) return;                              // uniform across the cluster
+
     if (tid == 0) {
-        mbar_init(bar_base, CS > 1 ? 1 : NW);
-        mbar_init(bar_base + 8, CS > 1 ? 1 : NW);
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                mbar_init(smem_u32(&mbars[g][p]), 1);
+                mbar_init(smem_u32(&lbars[g][p]), NW);
+            }
         mbar_fence_init();
         if (CS > 1) {
-            mbar_arrive_expect_tx(bar_base, NCAND * kCandBytes);
-            mbar_arrive_expect_tx(bar_base + 8, NCAND * kCandBytes);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) mbar_arrive_expect_tx(smem_u32(&mbars[g][p]), CS * kCandBytes);
         }
     }
     if (CS > 1) cluster_sync_all(); else __syncthreads();
@@ -88,142 +110,156 @@ fps_resident_kernel(const float* __restrict__ xyz, const int* __restrict__ offse
     const int r = u & (bs - 1);
     const int q = u >> bs_log2;
     const int tprio = (bitrev_low(r, bs_log2) << 14) | q;
-    const float* cxyz = xyz + 3 * static_cast<size_t>(start_n);
-    float* ctmp = tmp ? tmp + start_n : nullptr;
 
-    uint64_t X[PAIRS], Y[PAIRS], Z[PAIRS];
-    float t[SLOTS];
+    uint64_t X[G][PAIRS], Y[G][PAIRS], Z[G][PAIRS];
+    float t[G][SLOTS];
+    float ox[G], oy[G], oz[G];
 #pragma unroll
-    for (int p = 0; p < PAIRS; ++p) {
-        float c[2][3];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = (q * SLOTS + 2 * p + h) * bs + r;
-            const bool ok = j < n;
-            c[h][0] = ok ? __ldg(cxyz + 3 * static_cast<size_t>(j) + 0) : 0.f;
-            c[h][1] = ok ? __ldg(cxyz + 3 * static_cast<size_t>(j) + 1) : 0.f;
-            c[h][2] = ok ? __ldg(cxyz + 3 * static_cast<size_t>(j) + 2) : 0.f;
-            t[2 * p + h] = ok ? (ctmp ? ctmp[j] : 1e10f) : -1.0f;   // pads can never be a maximum
-        }
-        X[p] = pack2(c[0][0], c[1][0]);
-        Y[p] = pack2(c[0][1], c[1][1]);
-        Z[p] = pack2(c[0][2], c[1][2]);
-    }
-    float ox = __ldg(cxyz + 0), oy = __ldg(cxyz + 1), oz = __ldg(cxyz + 2);
-
-    for (int it = 1; it < m; ++it) {
-        const int par = it & 1;
-        const uint32_t bar = bar_base + 8 * par;
-        const uint64_t OX = pack2(ox, ox), OY = pack2(oy, oy), OZ = pack2(oz, oz);
-        float acc[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) acc[g] = -1.0f;
+    for (int g = 0; g < G; ++g) {
+        const float* cxyz = xyz + 3 * static_cast<size_t>(start_n[g]);
+        const float* ctmp = tmp ? tmp + start_n[g] : nullptr;
 #pragma unroll
         for (int p = 0; p < PAIRS; ++p) {
-            const uint64_t dx = sub2(X[p], OX), dy = sub2(Y[p], OY), dz = sub2(Z[p], OZ);
-            uint64_t d = mul2(dy, dy);
-            d = fma2(dx, dx, d);
-            d = fma2(dz, dz, d);
-            float dl, dh;
-            unpack2(d, dl, dh);
-            t[2 * p] = fminf(dl, t[2 * p]);
-            t[2 * p + 1] = fminf(dh, t[2 * p + 1]);
-            acc[p / PPG] = max3(acc[p / PPG], t[2 * p], t[2 * p + 1]);
-        }
-        float best = acc[0];
+            float c[2][3];
 #pragma unroll
-        for (int g = 1; g < NG; ++g) best = fmaxf(best, acc[g]);
-
-        // ---- warp candidate: max value, then smallest thread priority among the tied lanes ----
-        const int bi = __float_as_int(best);            // t >= 0 or -1: signed-int order == float order
-        const int wmax = __reduce_max_sync(FULL, bi);
-        const int wpri = __reduce_min_sync(FULL, bi == wmax ? tprio : INT_MAX);
-        if (bi == wmax && tprio == wpri) {              // exactly one lane
-            // Which slot?  The accumulator groups narrow the search to PPG pairs; within the
-            // group the lowest matching slot wins (the reference's strict '>' keeps the first).
-            int gsel = NG - 1;
-#pragma unroll
-            for (int g = NG - 2; g >= 0; --g)
-                if (acc[g] == best) gsel = g;
-            int psel = 0;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                if (g == gsel) {
-                    psel = (g + 1) * PPG - 1;
-#pragma unroll
-                    for (int p = (g + 1) * PPG - 2; p >= g * PPG; --p)
-                        if (t[2 * p] == best || t[2 * p + 1] == best) psel = p;
-                }
+            for (int h = 0; h < 2; ++h) {
+                const int j = (q * SLOTS + 2 * p + h) * bs + r;
+                const bool ok = j < n[g] && m[g] > 1;
+                c[h][0] = ok ? __ldg(cxyz + 3 * static_cast<size_t>(j) + 0) : 0.f;
+                c[h][1] = ok ? __ldg(cxyz + 3 * static_cast<size_t>(j) + 1) : 0.f;
+                c[h][2] = ok ? __ldg(cxyz + 3 * static_cast<size_t>(j) + 2) : 0.f;
+                t[g][2 * p + h] = ok ? (ctmp ? ctmp[j] : 1e10f) : -1.0f;   // pads can never be a maximum
             }
-            uint64_t px = 0, py = 0, pz = 0;
-            float tl = 0.f;
-            switch (psel) {
-#define TGN_FPS_PAIR(P_) case P_: if (P_ < PAIRS) { px = X[P_ < PAIRS ? P_ : 0]; py = Y[P_ < PAIRS ? P_ : 0]; pz = Z[P_ < PAIRS ? P_ : 0]; tl = t[P_ < PAIRS ? 2 * P_ : 0]; } break;
-                TGN_FPS_PAIR(0) TGN_FPS_PAIR(1) TGN_FPS_PAIR(2) TGN_FPS_PAIR(3) TGN_FPS_PAIR(4) TGN_FPS_PAIR(5)
-                TGN_FPS_PAIR(6) TGN_FPS_PAIR(7) TGN_FPS_PAIR(8) TGN_FPS_PAIR(9) TGN_FPS_PAIR(10) TGN_FPS_PAIR(11)
-#undef TGN_FPS_PAIR
-                default: break;
-            }
-            static_assert(PAIRS <= 12, "extend the pair switch");
-            const bool low = (tl == best);
-            const int sel = 2 * psel + (low ? 0 : 1);
-            float xl, xh, yl, yh, zl, zh;
-            unpack2(px, xl, xh); unpack2(py, yl, yh); unpack2(pz, zl, zh);
-            const float sx = low ? xl : xh, sy = low ? yl : yh, sz = low ? zl : zh;
-            const int j = (q * SLOTS + sel) * bs + r;
-            const int e = (rank * NW + warp) * kCandWords;
-            if (CS > 1) {
-                const uint32_t slot = smem_u32(&mailbox[par][e]);
-#pragma unroll
-                for (int dst = 0; dst < CS; ++dst) {
-                    const uint32_t ra = map_to_cta(slot, dst), rb = map_to_cta(bar, dst);
-                    st_async_v4(ra, static_cast<uint32_t>(bi), static_cast<uint32_t>(j), __float_as_uint(sx),
-                                __float_as_uint(sy), rb);
-                    st_async_b32(ra + 16, __float_as_uint(sz), rb);
-                }
-            } else {
-                uint32_t* slot = &mailbox[par][e];
-                *reinterpret_cast<uint4*>(slot) = make_uint4(static_cast<uint32_t>(bi), static_cast<uint32_t>(j),
-                                                             __float_as_uint(sx), __float_as_uint(sy));
-                slot[4] = __float_as_uint(sz);
-                mbar_arrive(bar);             // release.cta: the stores above are visible to waiters
-            }
+            X[g][p] = pack2(c[0][0], c[1][0]);
+            Y[g][p] = pack2(c[0][1], c[1][1]);
+            Z[g][p] = pack2(c[0][2], c[1][2]);
         }
-
-        // ---- wait for every warp of the cluster, then pick the global winner -------------------
-        mbar_wait(bar, ((it - 1) >> 1) & 1);
-        int cval = INT_MIN, ckey = INT_MAX, cent = 0;
-#pragma unroll
-        for (int e0 = 0; e0 < NCAND; e0 += 32) {
-            const int e = e0 + lane;
-            if (NCAND % 32 == 0 || e < NCAND) {
-                const uint2 vj = *reinterpret_cast<const uint2*>(&mailbox[par][e * kCandWords]);
-                const int v = static_cast<int>(vj.x), k = point_key(static_cast<int>(vj.y), bs_log2);
-                if (v > cval || (v == cval && k < ckey)) { cval = v; ckey = k; cent = e; }
-            }
-        }
-        const int gmax = __reduce_max_sync(FULL, cval);
-        const int gkey = __reduce_min_sync(FULL, cval == gmax ? ckey : INT_MAX);
-        const int src = __ffs(__ballot_sync(FULL, cval == gmax && ckey == gkey)) - 1;
-        const uint4 w0 = *reinterpret_cast<const uint4*>(&mailbox[par][cent * kCandWords]);
-        const uint32_t w1 = mailbox[par][cent * kCandWords + 4];
-        const int jstar = __shfl_sync(FULL, static_cast<int>(w0.y), src);
-        ox = __uint_as_float(__shfl_sync(FULL, w0.z, src));
-        oy = __uint_as_float(__shfl_sync(FULL, w0.w, src));
-        oz = __uint_as_float(__shfl_sync(FULL, w1, src));
-        if (tid == 0) {
-            if (rank == 0) idx[start_m + it] = start_n + jstar;
-            // Re-arm this parity's barrier for iteration it+2.  Nobody can complete bytes on that
-            // phase before receiving this CTA's candidates of iteration it+1, which are sent later.
-            if (CS > 1 && it + 2 < m) mbar_arrive_expect_tx(bar, NCAND * kCandBytes);
-        }
+        const bool any = m[g] > 1;
+        ox[g] = any ? __ldg(cxyz + 0) : 0.f;
+        oy[g] = any ? __ldg(cxyz + 1) : 0.f;
+        oz[g] = any ? __ldg(cxyz + 2) : 0.f;
     }
 
-    if (ctmp) {
+    // Winner of iteration `itp` of cloud g: wait for the mailbox, pick the best of the CS
+    // candidates, record it.  Executed by every warp (each needs the coordinates).
+    auto consume = [&](int g, int itp) {
+        const int par = itp & 1;
+        const uint32_t bar = smem_u32(&mbars[g][par]);
+        mbar_wait(bar, ((itp - 1) >> 1) & 1);
+        int cv = INT_MIN, ck = INT_MAX;
+        if (lane < CS) {
+            const uint2 vk = *reinterpret_cast<const uint2*>(&mailbox[g][par][lane * kCandWords]);
+            cv = static_cast<int>(vk.x);
+            ck = static_cast<int>(vk.y);
+        }
+        int src = 0;
+        if (CS > 1) {
+            const int gmax = __reduce_max_sync(FULL, cv);
+            const int gkey = __reduce_min_sync(FULL, cv == gmax ? ck : INT_MAX);
+            src = __ffs(__ballot_sync(FULL, cv == gmax && ck == gkey)) - 1;
+        }
+        const uint4 w0 = *reinterpret_cast<const uint4*>(&mailbox[g][par][src * kCandWords]);
+        const uint2 w1 = *reinterpret_cast<const uint2*>(&mailbox[g][par][src * kCandWords + 4]);
+        ox[g] = __uint_as_float(w0.z);
+        oy[g] = __uint_as_float(w0.w);
+        oz[g] = __uint_as_float(w1.x);
+        if (warp == g % NW && lane == 0) {
+            if (rank == 0) idx[start_m[g] + itp] = start_n[g] + static_cast<int>(w1.y);
+            // Re-arm this parity for iteration itp+2 before this warp publishes itp+1: nobody can
+            // complete bytes on that phase before receiving this CTA's candidate of itp+1.
+            if (CS > 1 && itp + 2 < m[g]) mbar_arrive_expect_tx(bar, CS * kCandBytes);
+        }
+    };
+
+    for (int it = 1; it < mmax; ++it) {
+        const int par = it & 1;
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int j = (q * SLOTS + s) * bs + r;
-            if (j < n) ctmp[j] = t[s];
+        for (int g = 0; g < G; ++g) {
+            if (it >= m[g]) continue;
+            if (it > 1) consume(g, it - 1);
+
+            // ---- update the running minima of cloud g and track this thread's first maximum ----
+            const uint64_t OX = pack2(ox[g], ox[g]), OY = pack2(oy[g], oy[g]), OZ = pack2(oz[g], oz[g]);
+            float best = -1.0f;
+            int bsel = 0;
+#pragma unroll
+            for (int p = 0; p < PAIRS; ++p) {
+                const uint64_t dx = sub2(X[g][p], OX), dy = sub2(Y[g][p], OY), dz = sub2(Z[g][p], OZ);
+                uint64_t d = mul2(dy, dy);
+                d = fma2(dx, dx, d);
+                d = fma2(dz, dz, d);
+                float dl, dh;
+                unpack2(d, dl, dh);
+                const float ta = fminf(dl, t[g][2 * p]);
+                t[g][2 * p] = ta;
+                if (ta > best) { best = ta; bsel = 2 * p; }             // strict '>': first maximum wins
+                const float tb = fminf(dh, t[g][2 * p + 1]);
+                t[g][2 * p + 1] = tb;
+                if (tb > best) { best = tb; bsel = 2 * p + 1; }
+            }
+
+            // ---- warp candidate: max value, then smallest thread priority among the tied lanes ----
+            const int bi = __float_as_int(best);        // t >= 0 or -1: signed-int order == float order
+            const int wmax = __reduce_max_sync(FULL, bi);
+            const int wpri = __reduce_min_sync(FULL, bi == wmax ? tprio : INT_MAX);
+            const uint32_t lbar = smem_u32(&lbars[g][par]);
+            if (bi == wmax && tprio == wpri) {          // exactly one lane
+                const int j = (q * SLOTS + bsel) * bs + r;
+                *reinterpret_cast<uint4*>(&wslot[g][par][warp * 4]) =
+                    make_uint4(static_cast<uint32_t>(bi), static_cast<uint32_t>(point_key(j, bs_log2)), static_cast<uint32_t>(j), 0u);
+                mbar_arrive(lbar);                      // release.cta: the store above is visible to the waiter
+            }
+
+            // ---- publisher warp of cloud g: CTA candidate -> every CTA of the cluster -----------------
+            if (warp == g % NW) {
+                mbar_wait(lbar, ((it - 1) >> 1) & 1);
+                int cv = INT_MIN, ck = INT_MAX, cj = 0;
+                if (NW == 32 || lane < NW) {
+                    const uint4 c = *reinterpret_cast<const uint4*>(&wslot[g][par][lane * 4]);
+                    cv = static_cast<int>(c.x); ck = static_cast<int>(c.y); cj = static_cast<int>(c.z);
+                }
+                const int cmax = __reduce_max_sync(FULL, cv);
+                const int ckey = __reduce_min_sync(FULL, cv == cmax ? ck : INT_MAX);
+                const int src = __ffs(__ballot_sync(FULL, cv == cmax && ck == ckey)) - 1;
+                const int jw = __shfl_sync(FULL, cj, src);
+                if (lane == 0) {
+                    const float* pw = xyz + 3 * (static_cast<size_t>(start_n[g]) + jw);
+                    const float wx = __ldg(pw), wy = __ldg(pw + 1), wz = __ldg(pw + 2);
+                    uint32_t* slot = &mailbox[g][par][rank * kCandWords];
+                    if (CS > 1) {
+                        const uint32_t sa = smem_u32(slot), ba = smem_u32(&mbars[g][par]);
+#pragma unroll
+                        for (int dst = 0; dst < CS; ++dst) {
+                            const uint32_t ra = map_to_cta(sa, dst), rb = map_to_cta(ba, dst);
+                            st_async_v4(ra, static_cast<uint32_t>(cmax), static_cast<uint32_t>(ckey), __float_as_uint(wx),
+                                        __float_as_uint(wy), rb);
+                            st_async_v2(ra + 16, __float_as_uint(wz), static_cast<uint32_t>(jw), rb);
+                        }
+                    } else {
+                        *reinterpret_cast<uint4*>(slot) = make_uint4(static_cast<uint32_t>(cmax), static_cast<uint32_t>(ckey),
+                                                                     __float_as_uint(wx), __float_as_uint(wy));
+                        *reinterpret_cast<uint2*>(slot + 4) = make_uint2(__float_as_uint(wz), static_cast<uint32_t>(jw));
+                        mbar_arrive(smem_u32(&mbars[g][par]));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        if (m[g] > 1) consume(g, m[g] - 1);             // winner of the last iteration
+
+    if (tmp) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (m[g] <= 1) continue;
+            float* ctmp = tmp + start_n[g];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int j = (q * SLOTS + s) * bs + r;
+                if (j < n[g]) ctmp[j] = t[g][s];
+            }
         }
     }
     if (CS > 1) cluster_sync_all();   // no CTA leaves while a peer may still address its shared memory
@@ -302,13 +338,13 @@ int ref_block_log2(int n)
     return l;
 }
 
-template <int T, int SLOTS, int CS>
+template <int T, int SLOTS, int CS, int G>
 int launch_resident(int b, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
                     int bs_log2, cudaStream_t stream)
 {
-    auto kern = fps_resident_kernel<T, SLOTS, CS>;
+    auto kern = fps_resident_kernel<T, SLOTS, CS, G>;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(b) * CS);
+    cfg.gridDim = dim3(static_cast<unsigned>((b + G - 1) / G) * CS);
     cfg.blockDim = dim3(T);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
@@ -319,58 +355,71 @@ int launch_resident(int b, const float* xyz, const int* offset, const int* new_o
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, offset, new_offset, tmp, idx, bs_log2);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, offset, new_offset, tmp, idx, b, bs_log2);
     if (e != cudaSuccess) {
-        set_error("fps_resident_kernel<%d,%d,%d> launch failed: %s", T, SLOTS, CS, cudaGetErrorString(e));
+        set_error("fps_resident_kernel<%d,%d,%d,%d> launch failed: %s", T, SLOTS, CS, G, cudaGetErrorString(e));
         (void)cudaGetLastError();
         return TGN_ERR_CUDA;
     }
     return check_launch("fps_resident_kernel");
 }
 
-struct FpsConfig { int T, SLOTS, CS; };
+struct FpsConfig { int T, SLOTS, CS, G; };
 
-// Smallest resident configuration that holds n_max points at cluster size cs (or {0,0,0}).
-FpsConfig pick_config(int n_max, int bs_log2, int cs)
+// (T, SLOTS per cloud, cluster size, clouds in flight per cluster); register budget:
+// 4 * SLOTS * G data registers per thread, 128 at T=512, 64 at T=1024.
+const FpsConfig kConfigs[] = {
+    {128, 4, 1, 1}, {256, 4, 1, 1}, {512, 4, 1, 1}, {1024, 4, 1, 1}, {1024, 8, 1, 1},
+    {512, 4, 2, 1}, {512, 8, 2, 1}, {512, 12, 2, 1}, {512, 16, 2, 1}, {512, 24, 2, 1},
+    {512, 4, 4, 1}, {512, 8, 4, 1}, {512, 12, 4, 1}, {512, 16, 4, 1}, {512, 24, 4, 1},
+    {512, 4, 8, 1}, {512, 8, 8, 1}, {512, 12, 8, 1}, {512, 16, 8, 1}, {512, 24, 8, 1},
+    // software-pipelined: two clouds per cluster
+    {512, 4, 1, 2}, {512, 8, 1, 2}, {512, 12, 1, 2},
+    {512, 4, 2, 2}, {512, 8, 2, 2}, {512, 12, 2, 2},
+    {512, 4, 4, 2}, {512, 8, 4, 2}, {512, 12, 4, 2},
+    {512, 8, 8, 2}, {512, 12, 8, 2},
+};
+
+// Smallest resident configuration that holds n_max points at cluster size cs with g clouds in flight.
+FpsConfig pick_config(int n_max, int bs_log2, int cs, int g)
 {
-    static const FpsConfig table[] = {
-        {128, 4, 1}, {256, 4, 1}, {512, 4, 1}, {1024, 4, 1}, {1024, 8, 1},
-        {512, 4, 2}, {512, 8, 2}, {512, 12, 2}, {512, 16, 2}, {512, 24, 2},
-        {512, 4, 4}, {512, 8, 4}, {512, 12, 4}, {512, 16, 4}, {512, 24, 4},
-        {512, 4, 8}, {512, 8, 8}, {512, 12, 8}, {512, 16, 8}, {512, 24, 8},
-    };
     const int bs = 1 << bs_log2;
-    for (const FpsConfig& c : table) {
-        if (c.CS != cs) continue;
+    for (const FpsConfig& c : kConfigs) {
+        if (c.CS != cs || c.G != g) continue;
         const int v = c.T * c.CS;
         if (v < bs) continue;
         const long long cap_slots = static_cast<long long>(v / bs) * c.SLOTS;     // slots per residue
-        if (cap_slots * bs >= n_max && cap_slots >= (n_max + bs - 1) / bs) return c;
+        if (cap_slots >= (n_max + bs - 1) / bs) return c;
     }
-    return {0, 0, 0};
+    return {0, 0, 0, 0};
 }
 
-#define TGN_FPS_CASE(T_, S_, C_)                                                                      \
-    if (c.T == T_ && c.SLOTS == S_ && c.CS == C_)                                                      \
-        return launch_resident<T_, S_, C_>(b, xyz, offset, new_offset, tmp, idx, bs_log2, stream);
+#define TGN_FPS_CASE(T_, S_, C_, G_)                                                                  \
+    if (c.T == T_ && c.SLOTS == S_ && c.CS == C_ && c.G == G_)                                         \
+        return launch_resident<T_, S_, C_, G_>(b, xyz, offset, new_offset, tmp, idx, bs_log2, stream);
 
 int dispatch_resident(const FpsConfig& c, int b, const float* xyz, const int* offset, const int* new_offset,
                       float* tmp, int* idx, int bs_log2, cudaStream_t stream)
 {
-    TGN_FPS_CASE(128, 4, 1) TGN_FPS_CASE(256, 4, 1) TGN_FPS_CASE(512, 4, 1) TGN_FPS_CASE(1024, 4, 1)
-    TGN_FPS_CASE(1024, 8, 1)
-    TGN_FPS_CASE(512, 4, 2) TGN_FPS_CASE(512, 8, 2) TGN_FPS_CASE(512, 12, 2) TGN_FPS_CASE(512, 16, 2)
-    TGN_FPS_CASE(512, 24, 2)
-    TGN_FPS_CASE(512, 4, 4) TGN_FPS_CASE(512, 8, 4) TGN_FPS_CASE(512, 12, 4) TGN_FPS_CASE(512, 16, 4)
-    TGN_FPS_CASE(512, 24, 4)
-    TGN_FPS_CASE(512, 4, 8) TGN_FPS_CASE(512, 8, 8) TGN_FPS_CASE(512, 12, 8) TGN_FPS_CASE(512, 16, 8)
-    TGN_FPS_CASE(512, 24, 8)
-    set_error("no resident FPS kernel for T=%d SLOTS=%d CS=%d", c.T, c.SLOTS, c.CS);
+    TGN_FPS_CASE(128, 4, 1, 1) TGN_FPS_CASE(256, 4, 1, 1) TGN_FPS_CASE(512, 4, 1, 1) TGN_FPS_CASE(1024, 4, 1, 1)
+    TGN_FPS_CASE(1024, 8, 1, 1)
+    TGN_FPS_CASE(512, 4, 2, 1) TGN_FPS_CASE(512, 8, 2, 1) TGN_FPS_CASE(512, 12, 2, 1) TGN_FPS_CASE(512, 16, 2, 1)
+    TGN_FPS_CASE(512, 24, 2, 1)
+    TGN_FPS_CASE(512, 4, 4, 1) TGN_FPS_CASE(512, 8, 4, 1) TGN_FPS_CASE(512, 12, 4, 1) TGN_FPS_CASE(512, 16, 4, 1)
+    TGN_FPS_CASE(512, 24, 4, 1)
+    TGN_FPS_CASE(512, 4, 8, 1) TGN_FPS_CASE(512, 8, 8, 1) TGN_FPS_CASE(512, 12, 8, 1) TGN_FPS_CASE(512, 16, 8, 1)
+    TGN_FPS_CASE(512, 24, 8, 1)
+    TGN_FPS_CASE(512, 4, 1, 2) TGN_FPS_CASE(512, 8, 1, 2) TGN_FPS_CASE(512, 12, 1, 2)
+    TGN_FPS_CASE(512, 4, 2, 2) TGN_FPS_CASE(512, 8, 2, 2) TGN_FPS_CASE(512, 12, 2, 2)
+    TGN_FPS_CASE(512, 4, 4, 2) TGN_FPS_CASE(512, 8, 4, 2) TGN_FPS_CASE(512, 12, 4, 2)
+    TGN_FPS_CASE(512, 8, 8, 2) TGN_FPS_CASE(512, 12, 8, 2)
+    set_error("no resident FPS kernel for T=%d SLOTS=%d CS=%d G=%d", c.T, c.SLOTS, c.CS, c.G);
     return TGN_ERR_INVALID;
 }
 
 }  // namespace
 
+// mode: 0 auto, -1 streaming kernel, otherwise 100*G + CS (G omitted = 1): force that shape.
 int fps_dispatch(int b, int n_max, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
                  int mode, cudaStream_t stream)
 {
@@ -382,25 +431,37 @@ int fps_dispatch(int b, int n_max, const float* xyz, const int* offset, const in
         fps_stream_kernel<<<b, 1024, 0, stream>>>(xyz, offset, new_offset, tmp, idx, bs_log2);
         return check_launch("fps_stream_kernel");
     }
-    FpsConfig cfg{0, 0, 0};
+    FpsConfig cfg{0, 0, 0, 0};
     if (mode > 0) {
-        cfg = pick_config(n_max, bs_log2, mode);
+        cfg = pick_config(n_max, bs_log2, mode % 100, std::max(1, mode / 100));
     } else {
-        // Throughput when the batch can fill the machine with the smallest feasible cluster,
-        // latency (wider clusters) when only a few clouds are in flight.
         const int sms = sm_count();
-        int first = 0;
-        for (int cs = 1; cs <= 8; cs *= 2)
-            if (pick_config(n_max, bs_log2, cs).T) { first = cs; break; }
-        if (first) {
-            int cs = first;
-            while (cs < 8 && static_cast<long long>(b) * cs * 2 <= sms && n_max / (cs * 2) >= 1024 &&
-                   pick_config(n_max, bs_log2, cs * 2).T)
-                cs *= 2;
-            cfg = pick_config(n_max, bs_log2, cs);
+        // Throughput shape: two clouds pipelined through the smallest cluster that holds them,
+        // when there are at least two clouds and the batch can occupy the machine that way.
+        if (b >= 2) {
+            for (int cs = 1; cs <= 8 && !cfg.T; cs *= 2) {
+                const FpsConfig c = pick_config(n_max, bs_log2, cs, 2);
+                if (c.T && static_cast<long long>((b + 1) / 2) * cs * 2 > sms / 2) cfg = c;
+                else if (c.T) break;
+            }
+        }
+        if (!cfg.T) {
+            // Latency shape: one cloud per cluster, widened while SMs are idle and each CTA still
+            // holds >= 1024 points.
+            int first = 0;
+            for (int cs = 1; cs <= 8; cs *= 2)
+                if (pick_config(n_max, bs_log2, cs, 1).T) { first = cs; break; }
+            if (first) {
+                int cs = first;
+                while (cs < 8 && static_cast<long long>(b) * cs * 2 <= sms && n_max / (cs * 2) >= 1024 &&
+                       pick_config(n_max, bs_log2, cs * 2, 1).T)
+                    cs *= 2;
+                cfg = pick_config(n_max, bs_log2, cs, 1);
+            }
         }
     }
     if (!cfg.T) {
+        if (mode > 0) { set_error("furthestsampling: no resident kernel of shape %d for n_max=%d", mode, n_max); return TGN_ERR_INVALID; }
         if (!tmp) {
             set_error("furthestsampling: n_max=%d exceeds the register-resident kernels and no tmp buffer was given", n_max);
             return TGN_ERR_INVALID;

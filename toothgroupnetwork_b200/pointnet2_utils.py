@@ -305,11 +305,18 @@ def _wants_grad(module: nn.Module, *tensors) -> bool:
     return any(p.requires_grad for p in module.parameters())
 
 
+def _fp32_convs():
+    """The library 1x1 convolutions of the unfused paths run in IEEE fp32: torch's default lets
+    cuDNN use TF32 (1e-3 relative), which would break the 1e-4 parity bound."""
+    return torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False)
+
+
 def _mlp_unfused(grouped: torch.Tensor, convs, bns) -> torch.Tensor:
     """grouped (B,S,K,C) -> (B,C_out,S): the reference's permute + conv/BN/ReLU + max (:227-237)."""
     h = grouped.permute(0, 3, 2, 1)
-    for conv, bn in zip(convs, bns):
-        h = F.relu(bn(conv(h)))
+    with _fp32_convs():
+        for conv, bn in zip(convs, bns):
+            h = F.relu(bn(conv(h)))
     return torch.max(h, 2)[0]
 
 
@@ -442,6 +449,7 @@ class PointNetFeaturePropagation(nn.Module):
         h = _transpose(interp)                                     # (B,D2,N)
         if points1 is not None:
             h = torch.cat([points1, h], dim=1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            h = F.relu(bn(conv(h)))
+        with _fp32_convs():
+            for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+                h = F.relu(bn(conv(h)))
         return h

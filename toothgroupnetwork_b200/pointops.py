@@ -33,7 +33,8 @@ def _need(t: torch.Tensor, dtype, what: str) -> None:
 def fps_packed(xyz: torch.Tensor, offset: torch.Tensor, new_offset: torch.Tensor, n_max: int, m_total: int,
                mode: int = 0) -> torch.Tensor:
     """FPS with the host-side sizes already known (no device->host sync).  ``mode``: 0 auto,
-    1/2/4/8 force that cluster size, -1 force the streaming kernel."""
+    -1 the streaming kernel, otherwise 100*G + CS forces a cluster of CS CTAs with G clouds in
+    flight (G omitted = 1), e.g. 8 or 204."""
     _need(xyz, torch.float32, "xyz")
     _need(offset, torch.int32, "offset")
     _need(new_offset, torch.int32, "new_offset")
