@@ -36,6 +36,9 @@ FPS_CASES = [
     ("tiny", lambda: [clouds.cube(12, 6), clouds.cube(1, 7), clouds.cube(5, 8)], [5, 1, 5]),
     ("crops16x3072", lambda: [clouds.dental_arch(3072, 10 + i)[0] for i in range(16)], [768] * 16),
     ("more_samples_than_unique", lambda: [clouds.with_duplicates(clouds.cube(40, 9), 9)], [80]),
+    ("raw_mesh_100k", lambda: [clouds.dental_arch(100000, 12)[0]], [1500]),                 # SURVEY 8(f) next-2 size
+    ("flat_and_tiny_extent", lambda: [clouds.cube(9000, 13) * torch.tensor([1.0, 1e-3, 0.0])], [700]),  # degenerate bbox
+    ("arch_dups_24k", lambda: [clouds.with_duplicates(clouds.dental_arch(12000, 14)[0], 14)], [2048]),
 ]
 
 
@@ -47,7 +50,7 @@ def _pack(cl, ms):
 
 
 @pytest.mark.parametrize("name,build,ms", FPS_CASES, ids=[c[0] for c in FPS_CASES])
-@pytest.mark.parametrize("mode", [0, 1, 2, 4, 8, 201, 202, 204, 208, -1])   # 100*G + CS, see tgn_furthestsampling
+@pytest.mark.parametrize("mode", [0, 1, 2, 4, 8, 201, 202, 204, 208, -1, -2])   # 100*G + CS, see tgn_furthestsampling
 def test_fps_matches_oracle(name, build, ms, mode):
     cl = build()
     xyz, offset, new_offset = _pack(cl, ms)

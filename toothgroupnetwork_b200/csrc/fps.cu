@@ -33,6 +33,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "fps.cuh"
 #include "tgn_b200.h"
 
 namespace tgn {
@@ -419,7 +420,8 @@ int dispatch_resident(const FpsConfig& c, int b, const float* xyz, const int* of
 
 }  // namespace
 
-// mode: 0 auto, -1 streaming kernel, otherwise 100*G + CS (G omitted = 1): force that shape.
+// mode: 0 auto, -1 streaming kernel, -2 bucket-pruned kernel, otherwise 100*G + CS (G omitted = 1):
+// force that register-resident shape.
 int fps_dispatch(int b, int n_max, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
                  int mode, cudaStream_t stream)
 {
@@ -431,6 +433,12 @@ int fps_dispatch(int b, int n_max, const float* xyz, const int* offset, const in
         fps_stream_kernel<<<b, 1024, 0, stream>>>(xyz, offset, new_offset, tmp, idx, bs_log2);
         return check_launch("fps_stream_kernel");
     }
+    // Auto: small clouds stay register-resident in one CTA (cheapest iteration); everything larger
+    // goes to the bucket-pruned kernel, which wins both on latency and on throughput.
+    if (mode == -2 || (mode == 0 && n_max > 4096 && n_max <= fps_bucket_max_points())) {
+        if (n_max > fps_bucket_max_points()) { set_error("furthestsampling: n_max=%d exceeds the bucket kernel", n_max); return TGN_ERR_INVALID; }
+        return fps_bucket_launch(b, n_max, xyz, offset, new_offset, tmp, idx, bs_log2, stream);
+    }
     FpsConfig cfg{0, 0, 0, 0};
     if (mode > 0) {
         cfg = pick_config(n_max, bs_log2, mode % 100, std::max(1, mode / 100));
@@ -438,7 +446,10 @@ int fps_dispatch(int b, int n_max, const float* xyz, const int* offset, const in
         const int sms = sm_count();
         // Throughput shape: two clouds pipelined through the smallest cluster that holds them,
         // when there are at least two clouds and the batch can occupy the machine that way.
-        if (b >= 2) {
+        // (measured on B200, profiles/: the pipelined shapes lose to one cloud per 2-CTA cluster at
+        //  24k points because per-warp reduction overhead doubles with the cluster size, so auto
+        //  mode does not pick them; they stay reachable through `mode` for experiments)
+        if (false && b >= 2) {
             for (int cs = 1; cs <= 8 && !cfg.T; cs *= 2) {
                 const FpsConfig c = pick_config(n_max, bs_log2, cs, 2);
                 if (c.T && static_cast<long long>((b + 1) / 2) * cs * 2 > sms / 2) cfg = c;
