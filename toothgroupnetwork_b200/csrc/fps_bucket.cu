@@ -37,8 +37,11 @@
 namespace tgn {
 namespace {
 
-constexpr int kT = 256;
+constexpr int kT = 256;            // sort kernel
 constexpr int kNW = kT / 32;
+constexpr int kMT = 512;           // main kernel
+constexpr int kMNW = kMT / 32;
+constexpr int kBatch = 4;          // buckets a warp keeps in flight (memory-level parallelism)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct BucketWs {
@@ -46,7 +49,7 @@ struct BucketWs {
     float* tval;      // [b][stride]   running minima in sorted order; pads -1
     uint2* key_a;     // [b][stride]   radix ping
     uint2* key_b;     // [b][stride]   radix pong
-    float4* bsphere;  // [b][nbmax]    bucket centre + inflated radius
+    float4* bsphere;  // [b][nbmax]    bucket centre + inflated radius (absolute slack included)
     int2* bvk;        // [b][nbmax]    initial cached candidate (value bits, tie key)
     float4* bxyzj;    // [b][nbmax]    initial cached candidate coordinates + original index
     float* scale;     // [b]           max |coordinate| of the cloud
@@ -58,6 +61,14 @@ __device__ __forceinline__ int bitrev_low(int v, int bits) {
 }
 __device__ __forceinline__ int point_key(int j, int bs_log2) {
     return (bitrev_low(j & ((1 << bs_log2) - 1), bs_log2) << 21) | (j >> bs_log2);
+}
+// Squared skip threshold of a bucket: with r' = inflated radius + absolute slack and M = max t of the
+// bucket, the bucket cannot change when D = |c - o| satisfies D > r' + sqrt(M * (1 + 1e-5)); both
+// sides are positive, so the test is D^2 > theta2 with theta2 rounded UP by the extra factors.
+__device__ __forceinline__ float skip_threshold2(float r_slack, float max_t) {
+    if (max_t < 0.f) return 0.f;                       // bucket of pads only (cannot happen)
+    const float th = (r_slack + sqrtf(max_t * 1.00002f)) * 1.000002f;
+    return th * th * 1.000002f;
 }
 __device__ __forceinline__ unsigned spread3(unsigned x) {   // 10 bits -> every third bit
     x = (x | (x << 16)) & 0x030000FFu;
@@ -244,18 +255,18 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
         const int wmax = __reduce_max_sync(FULL, bi);
         const int key = (bi == wmax && ok) ? point_key(j, bs_log2) : INT_MAX;
         const int wkey = __reduce_min_sync(FULL, key);
-        if (lane == 0) bs[bk] = make_float4(ccx, ccy, ccz, r * 1.00001f);
+        if (lane == 0) bs[bk] = make_float4(ccx, ccy, ccz, r * 1.00001f + 4e-6f * scale);
         if (bi == wmax && key == wkey) { bvk[bk] = make_int2(wmax, wkey); bxj[bk] = P; }
     }
 }
 
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kMT)
 fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                   float* tmp, int* __restrict__ idx, BucketWs ws, int bs_log2)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int nact;
-    __shared__ int4 wres[kNW];
+    __shared__ int4 wres[kMNW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x;
@@ -268,10 +279,11 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     if (m == 1) return;
 
     const int nb = ((n + 31) & ~31) >> 5;
-    float4* sph = reinterpret_cast<float4*>(dyn);                                   // [nbmax] centre + radius
+    float4* sph = reinterpret_cast<float4*>(dyn);                                   // [nbmax] centre, theta^2
     float4* cxyzj = sph + ws.nbmax;                                                 // [nbmax] candidate x,y,z,j
     int2* cvk = reinterpret_cast<int2*>(cxyzj + ws.nbmax);                          // [nbmax] candidate value bits, key
-    int* alist = reinterpret_cast<int*>(cvk + ws.nbmax);                            // [nbmax] active buckets
+    float* rad = reinterpret_cast<float*>(cvk + ws.nbmax);                          // [nbmax] inflated radius + slack
+    int* alist = reinterpret_cast<int*>(rad + ws.nbmax);                            // [nbmax] active buckets
 
     const float4* pts4 = ws.pts4 + static_cast<size_t>(cloud) * ws.stride;
     float* tval = ws.tval + static_cast<size_t>(cloud) * ws.stride;
@@ -279,24 +291,29 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
         const float4* gs = ws.bsphere + static_cast<size_t>(cloud) * ws.nbmax;
         const int2* gv = ws.bvk + static_cast<size_t>(cloud) * ws.nbmax;
         const float4* gx = ws.bxyzj + static_cast<size_t>(cloud) * ws.nbmax;
-        for (int bk = tid; bk < nb; bk += kT) { sph[bk] = gs[bk]; cvk[bk] = gv[bk]; cxyzj[bk] = gx[bk]; }
+        for (int bk = tid; bk < nb; bk += kMT) {
+            const float4 c = gs[bk];
+            const int2 v = gv[bk];
+            rad[bk] = c.w;
+            sph[bk] = make_float4(c.x, c.y, c.z, skip_threshold2(c.w, __int_as_float(v.x)));
+            cvk[bk] = v;
+            cxyzj[bk] = gx[bk];
+        }
         if (tid == 0) nact = 0;
     }
-    const float slack = 4e-6f * ws.scale[cloud];
     float ox = __ldg(xyz + 3 * static_cast<size_t>(start_n)), oy = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 1),
           oz = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 2);
     __syncthreads();
 
-    const int nb_round = (nb + kT - 1) / kT * kT;
+    const int nb_round = (nb + kMT - 1) / kMT * kMT;
     for (int it = 1; it < m; ++it) {
         // ---- (a) which buckets can change? --------------------------------------------------------------
-        for (int bk = tid; bk < nb_round; bk += kT) {
+        for (int bk = tid; bk < nb_round; bk += kMT) {
             bool act = false;
             if (bk < nb) {
                 const float4 c = sph[bk];
                 const float dx = c.x - ox, dy = c.y - oy, dz = c.z - oz;
-                const float L = sqrtf(dx * dx + dy * dy + dz * dz) - c.w - slack;
-                act = !(L > 0.f && L * L * 0.99999f > __int_as_float(cvk[bk].x));
+                act = !(dx * dx + dy * dy + dz * dz > c.w);        // D^2 > theta^2  ->  nothing can change
             }
             const unsigned mask = __ballot_sync(FULL, act);
             if (mask) {
@@ -309,32 +326,49 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
         __syncthreads();
         const int na = nact;
 
-        // ---- (b) exact update of the surviving buckets, one warp per bucket ---------------------------------
-        for (int a = warp; a < na; a += kNW) {
-            const int bk = alist[a];
-            const int p = bk * 32 + lane;
-            const float4 P = __ldg(pts4 + p);
-            const float tv = __ldcg(tval + p);
-            const float dx = P.x - ox, dy = P.y - oy, dz = P.z - oz;
-            float d = __fmul_rn(dy, dy);
-            d = __fmaf_rn(dx, dx, d);
-            d = __fmaf_rn(dz, dz, d);
-            const float nt = fminf(d, tv);
-            if (nt < tv) __stcg(tval + p, nt);
-            const int bi = __float_as_int(nt);          // pads stay at -1
-            const int wmax = __reduce_max_sync(FULL, bi);
-            const int key = (bi == wmax) ? point_key(__float_as_int(P.w), bs_log2) : INT_MAX;
-            const int wkey = __reduce_min_sync(FULL, key);
-            if (bi == wmax && key == wkey) { cvk[bk] = make_int2(wmax, wkey); cxyzj[bk] = P; }
+        // ---- (b) exact update of the surviving buckets: one warp per bucket, kBatch loads in flight ---------
+        for (int a0 = warp; a0 < na; a0 += kMNW * kBatch) {
+            int bk[kBatch];
+            float4 P[kBatch];
+            float tv[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int a = a0 + u * kMNW;
+                bk[u] = a < na ? alist[a] : -1;
+                if (bk[u] >= 0) {
+                    P[u] = __ldg(pts4 + bk[u] * 32 + lane);
+                    tv[u] = __ldcg(tval + bk[u] * 32 + lane);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (bk[u] < 0) continue;                      // warp-uniform
+                const float dx = P[u].x - ox, dy = P[u].y - oy, dz = P[u].z - oz;
+                float d = __fmul_rn(dy, dy);
+                d = __fmaf_rn(dx, dx, d);
+                d = __fmaf_rn(dz, dz, d);
+                const float nt = fminf(d, tv[u]);
+                if (nt < tv[u]) __stcg(tval + bk[u] * 32 + lane, nt);
+                const int bi = __float_as_int(nt);          // pads stay at -1
+                const int wmax = __reduce_max_sync(FULL, bi);
+                const int key = (bi == wmax) ? point_key(__float_as_int(P[u].w), bs_log2) : INT_MAX;
+                const int wkey = __reduce_min_sync(FULL, key);
+                if (bi == wmax && key == wkey) {
+                    cvk[bk[u]] = make_int2(wmax, wkey);
+                    cxyzj[bk[u]] = P[u];
+                    const float4 c = sph[bk[u]];
+                    sph[bk[u]] = make_float4(c.x, c.y, c.z, skip_threshold2(rad[bk[u]], nt));
+                }
+            }
         }
         __syncthreads();
         if (tid == 0) nact = 0;
 
         // ---- (c) arg-max over the cached candidates of all buckets -----------------------------------------
         int bv = INT_MIN, bkey = INT_MAX, bbk = 0;
-        for (int bk = tid; bk < nb; bk += kT) {
-            const int2 c = cvk[bk];
-            if (c.x > bv || (c.x == bv && c.y < bkey)) { bv = c.x; bkey = c.y; bbk = bk; }
+        for (int b2 = tid; b2 < nb; b2 += kMT) {
+            const int2 c = cvk[b2];
+            if (c.x > bv || (c.x == bv && c.y < bkey)) { bv = c.x; bkey = c.y; bbk = b2; }
         }
         {
             const int wv = __reduce_max_sync(FULL, bv);
@@ -344,7 +378,7 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
         __syncthreads();
         {
             int4 c = make_int4(INT_MIN, INT_MAX, 0, 0);
-            if (lane < kNW) c = wres[lane];
+            if (lane < kMNW) c = wres[lane];
             const int gv = __reduce_max_sync(FULL, c.x);
             const int gk = __reduce_min_sync(FULL, c.x == gv ? c.y : INT_MAX);
             const int src = __ffs(__ballot_sync(FULL, c.x == gv && c.y == gk)) - 1;
@@ -357,7 +391,7 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
 
     if (tmp) {
         __syncthreads();
-        for (int p = tid; p < n; p += kT) {
+        for (int p = tid; p < n; p += kMT) {
             const int j = __float_as_int(__ldg(&pts4[p].w));
             tmp[start_n + j] = __ldcg(tval + p);
         }
@@ -368,7 +402,7 @@ bool g_pool_configured = false;
 
 }  // namespace
 
-// Largest cloud the bucket kernel takes (bucket table in shared memory: 44 bytes per 32 points).
+// Largest cloud the bucket kernel takes (bucket table in shared memory: 48 bytes per 32 points).
 int fps_bucket_max_points() { return 4096 * 32; }
 
 int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
@@ -410,7 +444,7 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     fps_bucket_sort_kernel<<<b, kT, 0, stream>>>(xyz, offset, tmp, ws, bs_log2);
     int rc = check_launch("fps_bucket_sort_kernel");
     if (rc == TGN_OK) {
-        const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 2 + sizeof(int2) + sizeof(int));
+        const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 2 + sizeof(int2) + sizeof(float) + sizeof(int));
         static size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
             e = cudaFuncSetAttribute(fps_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -418,7 +452,7 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
             else configured = smem;
         }
         if (rc == TGN_OK) {
-            fps_bucket_kernel<<<b, kT, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
+            fps_bucket_kernel<<<b, kMT, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
             rc = check_launch("fps_bucket_kernel");
         }
     }
