@@ -3,11 +3,14 @@
 // Same contract as the fp32 engine in sa_mlp.cu, but the per-layer contraction
 //      D[128 rows, N] = A[128 rows, K] * W[N, K]^T
 // runs on the tensor cores with the accumulator in TENSOR MEMORY:
-//   * one CTA = 128 threads = 128 grouped rows (128/K groups); thread r owns row r end to end:
-//     it gathers its neighbour's [xyz_rel | feats] row, and after each layer reads ITS accumulator
-//     lane back with tcgen05.ld (32x32b: warp w owns TMEM lanes 32w..32w+31), applies
-//     bias + ReLU and writes the next layer's A operand -- the grouped tensor and the
-//     inter-layer activations never leave the SM;
+//   * a CTA is 4 independent TILE GROUPS of 128 threads; a group owns one 128-row tile (128/K
+//     neighbourhoods) at a time, thread r of the group owns row r end to end: it gathers its
+//     neighbour's [xyz_rel | feats] row, and after each layer reads ITS accumulator lane back with
+//     tcgen05.ld (32x32b: warp w owns TMEM lanes 32(w%4)..+31), applies bias + ReLU and writes
+//     the next layer's A operand -- the grouped tensor and the inter-layer activations never
+//     leave the SM.  The four groups share the weights but nothing else (own TMEM columns, own
+//     operand buffers, own mbarrier, named barriers instead of __syncthreads), so while one group
+//     waits for its gather or its MMAs the others fill the issue slots and the tensor pipe;
 //   * operands live in shared memory in the canonical K-major, no-swizzle UMMA layout
 //     (8x16-byte core matrices; element (r,k) at (k/4)*LBO + r*16 + (k%4)*4 with SBO = 128 B), which a
 //     row-per-thread writer fills with conflict-free 16-byte stores;
@@ -15,7 +18,9 @@
 //     K-step issues three kind::tf32 MMAs (hi*hi + lo*hi + hi*lo) into the same accumulator
 //     ("3xTF32"), so the result carries ~2^-21 relative error instead of tf32's 2^-10 -- the
 //     reference's own default for these 1x1 convolutions is plain TF32;
-//   * one elected thread issues the MMAs and tcgen05.commit's an mbarrier the 128 threads wait on.
+//   * one elected thread per group issues the MMAs and tcgen05.commit's the group's mbarrier;
+//   * the max over the K rows of a neighbourhood is a CREDUX per output channel when K is 16 or 32
+//     (the rows of a neighbourhood are the lanes of one warp), a shared-memory pass otherwise.
 // Weights are split and laid out once per CTA; CTAs are persistent over tiles.
 #include <algorithm>
 
@@ -26,18 +31,21 @@
 namespace tgn {
 namespace {
 
-constexpr int kRows = 128;
-constexpr int kThreads = 128;
-constexpr uint32_t kTmemCols = 128;
+constexpr int kRows = 128;                            // rows of a tile = threads of a tile group
+constexpr int kGroups = 4;
+constexpr int kThreads = kRows * kGroups;
 constexpr uint32_t kChunkStrideA = kRows * 16;        // LBO of the A operand: one 16-byte K-chunk of all rows
+constexpr unsigned FULL = 0xffffffffu;
 
 struct TcLayout {
     int kpad[kSaMaxLayers];          // K of layer l, multiple of 8
     int npad[kSaMaxLayers];          // N of layer l, multiple of 16
     uint32_t w_hi[kSaMaxLayers], w_lo[kSaMaxLayers], bias[kSaMaxLayers];   // byte offsets in dynamic smem
-    uint32_t a_hi, a_lo;             // A operands; a_hi doubles as the fp32 staging area of the last layer
-    uint32_t misc;                   // tmem base (u32) + mbarrier (u64)
+    uint32_t a_hi[kGroups], a_lo[kGroups];   // per group A operands; a_hi doubles as fp32 staging for generic K
+    uint32_t part[kGroups];          // per group: up to 8 per-warp partial maxima rows of npad floats
+    uint32_t misc;                   // tmem base (u32) @0, group mbarriers (u64) @8+8g
     uint32_t total;
+    uint32_t tmem_cols, group_cols;
     int tiles_per_cloud, gpt, stage_stride;
 };
 
@@ -66,6 +74,7 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kRows) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -100,23 +109,22 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = tid / kRows;                 // tile group
+    const int r = tid - g * kRows;             // row inside the tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + lay.misc);
-    const uint32_t bar = sbase + lay.misc + 8;
+    const uint32_t bar = sbase + lay.misc + 8 + 8 * g;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + lay.misc), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + lay.misc), "r"(lay.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
+    if (r == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     // ---- weights: split into tf32 hi/lo, canonical K-major layout (LBO = npad*16, SBO = 128) -------
     for (int l = 0; l < p.L; ++l) {
         const int cin = p.ch[l], cout = p.ch[l + 1], kp = lay.kpad[l], np = lay.npad[l];
@@ -136,13 +144,19 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t tmem_base = *tmem_slot + g * lay.group_cols;                       // this group's accumulator columns
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t a_hi = sbase + lay.a_hi[g], a_lo = sbase + lay.a_lo[g];
     uint32_t phase = 0;
 
     const int cin0 = p.ch[0];
+    const int cout_last = p.ch[p.L];
     const int total_tiles = lay.tiles_per_cloud * p.B;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tile_step = gridDim.x * kGroups;
+    const bool lane_max = (p.K == 16 || p.K == 32 || p.K == 64 || p.K == 128);
+    float* part = reinterpret_cast<float*>(smem + lay.part[g]);
+
+    for (int tile = blockIdx.x * kGroups + g; tile < total_tiles; tile += tile_step) {
         const int b = tile / lay.tiles_per_cloud;
         const int s0 = (tile - b * lay.tiles_per_cloud) * lay.gpt;
         const int groups = min(lay.gpt, p.S - s0);
@@ -150,7 +164,6 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 
         // ---- layer-0 operand: this thread's grouped row --------------------------------------------
         {
-            const int r = tid;
             int j = -1, s = s0;
             if (r < rows) {
                 s = s0 + r / p.K;
@@ -174,8 +187,8 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                     split_tf32(v, hi[i], lo[i]);
                 }
                 const uint32_t off = kc * kChunkStrideA + r * 16;
-                st_shared_v4(sbase + lay.a_hi + off, hi[0], hi[1], hi[2], hi[3]);
-                st_shared_v4(sbase + lay.a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+                st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
             }
         }
 
@@ -183,21 +196,21 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             const int kp = lay.kpad[l], np = lay.npad[l];
             proxy_fence_async();           // this thread's operand stores -> visible to the tensor core
             tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
+            group_sync(g);
+            if (r == 0) {
                 tc_fence_after();
                 const uint32_t idesc = make_idesc_tf32(np);
                 const uint32_t lbo_b = static_cast<uint32_t>(np) * 16;
                 for (int ks = 0; ks < kp / 8; ++ks) {
-                    const uint64_t a_hi = make_smem_desc(sbase + lay.a_hi + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
-                    const uint64_t a_lo = make_smem_desc(sbase + lay.a_lo + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
-                    const uint64_t b_hi = make_smem_desc(sbase + lay.w_hi[l] + ks * 2 * lbo_b, lbo_b, 128);
-                    const uint64_t b_lo = make_smem_desc(sbase + lay.w_lo[l] + ks * 2 * lbo_b, lbo_b, 128);
-                    mma_tf32_ss(tmem_base, a_hi, b_hi, idesc, ks > 0);
-                    mma_tf32_ss(tmem_base, a_lo, b_hi, idesc, true);
-                    mma_tf32_ss(tmem_base, a_hi, b_lo, idesc, true);
+                    const uint64_t d_ahi = make_smem_desc(a_hi + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
+                    const uint64_t d_alo = make_smem_desc(a_lo + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
+                    const uint64_t d_bhi = make_smem_desc(sbase + lay.w_hi[l] + ks * 2 * lbo_b, lbo_b, 128);
+                    const uint64_t d_blo = make_smem_desc(sbase + lay.w_lo[l] + ks * 2 * lbo_b, lbo_b, 128);
+                    mma_tf32_ss(tmem_base, d_ahi, d_bhi, idesc, ks > 0);
+                    mma_tf32_ss(tmem_base, d_alo, d_bhi, idesc, true);
+                    mma_tf32_ss(tmem_base, d_ahi, d_blo, idesc, true);
                 }
-                mma_commit(bar);           // arrives on the mbarrier when the MMAs above have completed
+                mma_commit(bar);           // arrives on the group's mbarrier when the MMAs above have completed
             }
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -205,7 +218,6 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 
             const float* bs = reinterpret_cast<const float*>(smem + lay.bias[l]);
             const bool last = (l == p.L - 1);
-            float* stage = reinterpret_cast<float*>(smem + lay.a_hi);
             for (int c0 = 0; c0 < np; c0 += 32) {
                 uint32_t v[32];
                 const bool full = np - c0 >= 32;             // np is a multiple of 16: a chunk is 32 or 16 wide
@@ -219,48 +231,85 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                                 split_tf32(fmaxf(__uint_as_float(v[i + u]) + bs[c0 + i + u], 0.f), hi[u], lo[u]);
-                            const uint32_t off = static_cast<uint32_t>((c0 + i) >> 2) * kChunkStrideA + tid * 16;
-                            st_shared_v4(sbase + lay.a_hi + off, hi[0], hi[1], hi[2], hi[3]);
-                            st_shared_v4(sbase + lay.a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+                            const uint32_t off = static_cast<uint32_t>((c0 + i) >> 2) * kChunkStrideA + r * 16;
+                            st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                            st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
+                } else if (lane_max) {
+                    // 32 rows of a neighbourhood (or 2 x 16) are the lanes of this warp: one CREDUX per
+                    // channel gives the warp's partial maximum.  Post-ReLU values are >= 0, so signed-int
+                    // order == float order; rows beyond `rows` contribute 0, the identity.
+                    float keep_a = 0.f, keep_b = 0.f;       // lane i keeps channel c0+i (second half-warp in _b)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i < 16 || full) {
+                            float x = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f);
+                            if (r >= rows) x = 0.f;
+                            if (p.K != 16) {
+                                const int mx = __reduce_max_sync(FULL, __float_as_int(x));
+                                if (lane == i) keep_a = __int_as_float(mx);
+                            } else {
+                                const int ma = __reduce_max_sync(FULL, lane < 16 ? __float_as_int(x) : 0);
+                                const int mb = __reduce_max_sync(FULL, lane >= 16 ? __float_as_int(x) : 0);
+                                if (lane == i) { keep_a = __int_as_float(ma); keep_b = __int_as_float(mb); }
+                            }
+                        }
+                    }
+                    if (full || lane < 16) {
+                        const int wq = warp & 3;
+                        if (p.K != 16) part[wq * np + c0 + lane] = keep_a;
+                        else { part[(2 * wq) * np + c0 + lane] = keep_a; part[(2 * wq + 1) * np + c0 + lane] = keep_b; }
+                    }
                 } else {
+                    float* stage = reinterpret_cast<float*>(smem + lay.a_hi[g]);
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (i < 16 || full)
-                            stage[tid * lay.stage_stride + c0 + i] = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f);
+                            stage[r * lay.stage_stride + c0 + i] = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f);
                 }
             }
             tc_fence_before();             // TMEM reads done before the next layer's MMAs overwrite D
         }
-        __syncthreads();
 
-        // ---- max over the K rows of each group, channel-first store ---------------------------------
-        {
-            const int cout = p.ch[p.L];
-            const float* stage = reinterpret_cast<const float*>(smem + lay.a_hi);
+        if (lane_max) {
+            // ---- combine the per-warp partial maxima of each neighbourhood, channel-first store -----------
+            group_sync(g);
+            const int np = lay.npad[p.L - 1];
+            const int ppn = p.K == 16 ? 1 : p.K / 32;          // partial rows per neighbourhood
             float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
-            for (int e = tid; e < groups * cout; e += kThreads) {
-                const int g = e / cout, co = e - g * cout;
-                float m = stage[(g * p.K) * lay.stage_stride + co];
-                for (int k = 1; k < p.K; ++k) m = fmaxf(m, stage[(g * p.K + k) * lay.stage_stride + co]);
-                ob[static_cast<size_t>(co) * p.S + s0 + g] = m;
+            for (int e = r; e < groups * cout_last; e += kRows) {
+                const int co = e / groups, sg = e - co * groups;
+                float m = part[(sg * ppn) * np + co];
+                for (int q = 1; q < ppn; ++q) m = fmaxf(m, part[(sg * ppn + q) * np + co]);
+                ob[static_cast<size_t>(co) * p.S + s0 + sg] = m;
             }
+        } else {
+            // ---- generic K: max over the K rows of each neighbourhood through shared memory -------------
+            group_sync(g);
+            const float* stage = reinterpret_cast<const float*>(smem + lay.a_hi[g]);
+            float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
+            for (int e = r; e < groups * cout_last; e += kRows) {
+                const int sg = e / cout_last, co = e - sg * cout_last;
+                float m = stage[(sg * p.K) * lay.stage_stride + co];
+                for (int k = 1; k < p.K; ++k) m = fmaxf(m, stage[(sg * p.K + k) * lay.stage_stride + co]);
+                ob[static_cast<size_t>(co) * p.S + s0 + sg] = m;
+            }
+            group_sync(g);                 // staging area becomes the next tile's A operand
         }
-        __syncthreads();                   // staging area becomes the next tile's A operand
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(lay.tmem_cols) : "memory");
     }
 }
 
 bool make_layout(const SaParams& p, TcLayout& lay)
 {
     if (p.K > kRows || p.K < 1) return false;
-    int kmax = 0, nlast = 0;
+    int kmax = 0, nmax = 0, nlast = 0;
     uint32_t off = 0;
     auto take = [&off](uint32_t bytes, uint32_t align) {
         off = (off + align - 1) / align * align;
@@ -273,24 +322,31 @@ bool make_layout(const SaParams& p, TcLayout& lay)
         lay.npad[l] = (p.ch[l + 1] + 15) / 16 * 16;
         if (lay.npad[l] > 128 || lay.kpad[l] > 128) return false;
         kmax = std::max(kmax, lay.kpad[l]);
+        nmax = std::max(nmax, lay.npad[l]);
         nlast = lay.npad[l];
     }
     lay.stage_stride = nlast + 1;
+    const bool lane_max = (p.K == 16 || p.K == 32 || p.K == 64 || p.K == 128);
     const uint32_t a_bytes = static_cast<uint32_t>(kmax / 4) * kChunkStrideA;
-    const uint32_t stage_bytes = static_cast<uint32_t>(kRows) * lay.stage_stride * 4;
-    lay.a_hi = take(std::max(a_bytes, stage_bytes), 1024);
-    lay.a_lo = take(a_bytes, 1024);
+    const uint32_t stage_bytes = lane_max ? 0u : static_cast<uint32_t>(kRows) * lay.stage_stride * 4;
+    for (int g = 0; g < kGroups; ++g) {
+        lay.a_hi[g] = take(std::max(a_bytes, stage_bytes), 128);
+        lay.a_lo[g] = take(a_bytes, 128);
+        lay.part[g] = take(lane_max ? 8u * nlast * 4u : 0u, 16);
+    }
     for (int l = 0; l < p.L; ++l) {
         const uint32_t wb = static_cast<uint32_t>(lay.npad[l]) * lay.kpad[l] * 4;
         lay.w_hi[l] = take(wb, 128);
         lay.w_lo[l] = take(wb, 128);
         lay.bias[l] = take(lay.npad[l] * 4, 16);
     }
-    lay.misc = take(16, 16);
+    lay.misc = take(8 + 8 * kGroups, 16);
     lay.total = off;
+    lay.group_cols = nmax <= 32 ? 32 : (nmax <= 64 ? 64 : 128);
+    lay.tmem_cols = lay.group_cols * kGroups;          // 128, 256 or 512: a power of two >= 32
     lay.gpt = kRows / p.K;
     lay.tiles_per_cloud = (p.S + lay.gpt - 1) / lay.gpt;
-    return lay.total <= 200 * 1024;
+    return lay.total <= 220 * 1024;
 }
 
 }  // namespace
@@ -311,9 +367,9 @@ int sa_mlp_tc_launch(SaParams p, cudaStream_t st)
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
         configured = lay.total;
     }
-    const int per_sm = std::max(1, std::min<int>(4, static_cast<int>((220u * 1024u) / (lay.total + 1024u))));
+    // one persistent CTA (4 tile groups, the whole TMEM budget of its accumulators) per SM
     const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
-    const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(sm_count()) * per_sm));
+    const int grid = static_cast<int>(std::min<long long>((tiles + kGroups - 1) / kGroups, sm_count()));
     sa_mlp_tc_kernel<<<grid, kThreads, lay.total, st>>>(p, lay);
     return check_launch("sa_mlp_tc_kernel");
 }
