@@ -93,6 +93,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Same, but a waiting warp yields its issue slots between probes (for long waits next to busy warps).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 // Asynchronous remote store that also completes `bytes` on the destination CTA's mbarrier
 // (both addresses are shared::cluster addresses obtained with map_to_cta).
 __device__ __forceinline__ void st_async_v4(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar) {

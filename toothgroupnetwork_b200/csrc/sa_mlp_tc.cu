@@ -155,6 +155,17 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
     const int tile_step = gridDim.x * kGroups;
     const bool lane_max = (p.K == 16 || p.K == 32 || p.K == 64 || p.K == 128);
     float* part = reinterpret_cast<float*>(smem + lay.part[g]);
+    const uint64_t desc_a_hi = make_smem_desc(a_hi, kChunkStrideA, 128);
+    const uint64_t desc_a_lo = make_smem_desc(a_lo, kChunkStrideA, 128);
+    int j_next = -1;
+    {
+        const int t0 = blockIdx.x * kGroups + g;
+        if (t0 < total_tiles) {
+            const int b0 = t0 / lay.tiles_per_cloud;
+            const int s00 = (t0 - b0 * lay.tiles_per_cloud) * lay.gpt;
+            if (r < min(lay.gpt, p.S - s00) * p.K) j_next = __ldg(p.gidx + (static_cast<size_t>(b0) * p.S + s00) * p.K + r);
+        }
+    }
 
     for (int tile = blockIdx.x * kGroups + g; tile < total_tiles; tile += tile_step) {
         const int b = tile / lay.tiles_per_cloud;
@@ -164,31 +175,42 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 
         // ---- layer-0 operand: this thread's grouped row --------------------------------------------
         {
-            int j = -1, s = s0;
-            if (r < rows) {
-                s = s0 + r / p.K;
-                j = __ldg(p.gidx + (static_cast<size_t>(b) * p.S + s0) * p.K + r);
-                if (j < 0 || j >= p.N) j = -1;
-            }
-            const float* px = p.xyz + 3 * (static_cast<size_t>(b) * p.N + (j < 0 ? 0 : j));
+            int j = j_next;                               // index prefetched while the previous tile computed
+            const int s = s0 + (r < rows ? r / p.K : 0);
+            if (r >= rows || j < 0 || j >= p.N) j = -1;
+            const int jj = j < 0 ? 0 : j;
+            const float* px = p.xyz + 3 * (static_cast<size_t>(b) * p.N + jj);
             const float* pc = p.new_xyz + 3 * (static_cast<size_t>(b) * p.S + s);
-            const float* pf = p.feats ? p.feats + (static_cast<size_t>(b) * p.N + (j < 0 ? 0 : j)) * p.D : nullptr;
+            const float* pf = p.feats ? p.feats + (static_cast<size_t>(b) * p.N + jj) * p.D : px;
+            const float rel0 = __fsub_rn(__ldg(px), __ldg(pc)), rel1 = __fsub_rn(__ldg(px + 1), __ldg(pc + 1)),
+                        rel2 = __fsub_rn(__ldg(px + 2), __ldg(pc + 2));
+            const int xoff = p.xyz_first ? 0 : p.D;       // first channel of the xyz_rel block
+            const int foff = p.xyz_first ? 3 : 0;         // first channel of the feature block
             for (int kc = 0; kc < lay.kpad[0] / 4; ++kc) {
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = 4 * kc + i;
-                    float v = 0.f;
-                    if (j >= 0 && c < cin0) {
-                        const int xc = p.xyz_first ? c : c - p.D;
-                        if (xc >= 0 && xc < 3) v = __fsub_rn(__ldg(px + xc), __ldg(pc + xc));
-                        else v = __ldg(pf + (p.xyz_first ? c - 3 : c));
+                    const int xc = c - xoff;
+                    float v = xc == 0 ? rel0 : (xc == 1 ? rel1 : rel2);
+                    if (static_cast<unsigned>(xc) > 2u) {
+                        const unsigned fc = static_cast<unsigned>(c - foff);
+                        v = fc < static_cast<unsigned>(p.D) ? __ldg(pf + fc) : 0.f;
                     }
+                    if (j < 0) v = 0.f;
                     split_tf32(v, hi[i], lo[i]);
                 }
                 const uint32_t off = kc * kChunkStrideA + r * 16;
                 st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
                 st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+            }
+            // prefetch the neighbour index of this thread's row in the group's next tile
+            const int nt = tile + tile_step;
+            j_next = -1;
+            if (nt < total_tiles) {
+                const int nb = nt / lay.tiles_per_cloud;
+                const int ns0 = (nt - nb * lay.tiles_per_cloud) * lay.gpt;
+                if (r < min(lay.gpt, p.S - ns0) * p.K) j_next = __ldg(p.gidx + (static_cast<size_t>(nb) * p.S + ns0) * p.K + r);
             }
         }
 
@@ -199,20 +221,24 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             group_sync(g);
             if (r == 0) {
                 tc_fence_after();
+                // The start-address field is the low 14 bits (units of 16 B): a K-step advances it by a
+                // constant, so the descriptors are built once per layer and bumped by an add.
                 const uint32_t idesc = make_idesc_tf32(np);
                 const uint32_t lbo_b = static_cast<uint32_t>(np) * 16;
-                for (int ks = 0; ks < kp / 8; ++ks) {
-                    const uint64_t d_ahi = make_smem_desc(a_hi + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
-                    const uint64_t d_alo = make_smem_desc(a_lo + ks * 2 * kChunkStrideA, kChunkStrideA, 128);
-                    const uint64_t d_bhi = make_smem_desc(sbase + lay.w_hi[l] + ks * 2 * lbo_b, lbo_b, 128);
-                    const uint64_t d_blo = make_smem_desc(sbase + lay.w_lo[l] + ks * 2 * lbo_b, lbo_b, 128);
+                uint64_t d_ahi = desc_a_hi, d_alo = desc_a_lo;
+                uint64_t d_bhi = make_smem_desc(sbase + lay.w_hi[l], lbo_b, 128);
+                uint64_t d_blo = make_smem_desc(sbase + lay.w_lo[l], lbo_b, 128);
+                const uint64_t step_a = (2 * kChunkStrideA) >> 4, step_b = (2 * lbo_b) >> 4;
+                const int nks = kp / 8;
+                for (int ks = 0; ks < nks; ++ks) {
                     mma_tf32_ss(tmem_base, d_ahi, d_bhi, idesc, ks > 0);
                     mma_tf32_ss(tmem_base, d_alo, d_bhi, idesc, true);
                     mma_tf32_ss(tmem_base, d_ahi, d_blo, idesc, true);
+                    d_ahi += step_a; d_alo += step_a; d_bhi += step_b; d_blo += step_b;
                 }
                 mma_commit(bar);           // arrives on the group's mbarrier when the MMAs above have completed
             }
-            mbar_wait(bar, phase);
+            mbar_wait_relaxed(bar, phase);
             phase ^= 1;
             tc_fence_after();
 
@@ -240,26 +266,30 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                     // 32 rows of a neighbourhood (or 2 x 16) are the lanes of this warp: one CREDUX per
                     // channel gives the warp's partial maximum.  Post-ReLU values are >= 0, so signed-int
                     // order == float order; rows beyond `rows` contribute 0, the identity.
-                    float keep_a = 0.f, keep_b = 0.f;       // lane i keeps channel c0+i (second half-warp in _b)
+                    const int wq = warp & 3;
+                    const float live = r < rows ? 1.f : 0.f;  // x * live: exact for the rows that count, 0 else
+                    if (p.K != 16) {
+                        float* dst = part + wq * np + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i < 16 || full) {
-                            float x = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f);
-                            if (r >= rows) x = 0.f;
-                            if (p.K != 16) {
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < 16 || full) {
+                                const float x = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f) * live;
                                 const int mx = __reduce_max_sync(FULL, __float_as_int(x));
-                                if (lane == i) keep_a = __int_as_float(mx);
-                            } else {
-                                const int ma = __reduce_max_sync(FULL, lane < 16 ? __float_as_int(x) : 0);
-                                const int mb = __reduce_max_sync(FULL, lane >= 16 ? __float_as_int(x) : 0);
-                                if (lane == i) { keep_a = __int_as_float(ma); keep_b = __int_as_float(mb); }
+                                if (lane == 0) dst[i] = __int_as_float(mx);
                             }
                         }
-                    }
-                    if (full || lane < 16) {
-                        const int wq = warp & 3;
-                        if (p.K != 16) part[wq * np + c0 + lane] = keep_a;
-                        else { part[(2 * wq) * np + c0 + lane] = keep_a; part[(2 * wq + 1) * np + c0 + lane] = keep_b; }
+                    } else {
+                        float* da = part + (2 * wq) * np + c0;
+                        float* db = part + (2 * wq + 1) * np + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < 16 || full) {
+                                const float x = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f) * live;
+                                const int ma = __reduce_max_sync(FULL, lane < 16 ? __float_as_int(x) : 0);
+                                const int mb = __reduce_max_sync(FULL, lane >= 16 ? __float_as_int(x) : 0);
+                                if (lane == 0) { da[i] = __int_as_float(ma); db[i] = __int_as_float(mb); }
+                            }
+                        }
                     }
                 } else {
                     float* stage = reinterpret_cast<float*>(smem + lay.a_hi[g]);
