@@ -6,27 +6,28 @@
 //
 //  * prologue kernel: the cloud is sorted by a 21-bit Morton code (stable LSD radix sort, three
 //    7-bit passes, one CTA per cloud) so that every 32 consecutive points -- a BUCKET, exactly one
-//    coalesced 512-byte float4 row -- are spatial neighbours; each bucket gets a bounding sphere.
-//  * main kernel (one CTA per cloud, several CTAs per SM): per iteration
-//      (a) every bucket is tested against the new sample o:  with D = |c_b - o| and the inflated
-//          radius r_b, every point p of the bucket has |p - o| >= D - r_b, so if
-//          (D - r_b - slack)^2 * (1 - 1e-5) > max_t(bucket) the update min(t, |p-o|^2) cannot change
-//          any t of the bucket (the slack terms dominate every fp32 rounding error involved; see
-//          DESIGN.md "pruning is conservative") and the bucket is skipped;
-//      (b) one warp per surviving bucket re-evaluates its 32 points with the reference's exact
-//          arithmetic (FMUL dy*dy, FFMA dx*dx+., FFMA dz*dz+., FMNMX), writes back changed minima and
-//          refreshes the bucket's cached candidate (max t, tie key, coordinates);
-//      (c) the block arg-max runs over the cached candidates of ALL buckets (two CREDUX levels).
-//    Ties are resolved by the reference's order (bitrev(j mod BS), j div BS) on ORIGINAL indices,
-//    carried in the w component of each sorted point, so the result does not depend on the
-//    internal order.
+//    coalesced 512-byte float4 row -- are spatial neighbours; each bucket gets an axis-aligned
+//    bounding box (inflated by an absolute slack).
+//  * main kernel (one CTA of 16 warps per cloud, several CTAs per SM); warp w OWNS the contiguous
+//    bucket range [w*R, (w+1)*R) and caches its best candidate and the union box of the range.
+//    Per iteration, with o the new sample:
+//      (a) owner warps test their range box, then their buckets: for every point p of a box,
+//          |p - o|^2 >= dist^2(o, box), so if dist^2(o, box) > max_t(box) * (1 + 2e-5) the update
+//          min(t, |p-o|^2) cannot change any t inside (the slack terms dominate every fp32 rounding
+//          error involved; DESIGN.md "pruning is conservative") and the box is skipped;
+//      (b) surviving buckets are spread over all warps, one warp per bucket, four loads in flight: the
+//          32 points are re-evaluated with the reference's exact arithmetic (FMUL dy*dy,
+//          FFMA dx*dx+., FFMA dz*dz+., FMNMX), changed minima are written back and the bucket's
+//          cached candidate (max t, tie key, coordinates) is refreshed;
+//      (c) owner warps whose range was touched refresh their range candidate; the block arg-max is
+//          one CREDUX pair over the 16 range candidates.
+//    Ties are resolved by the reference's order (bitrev(j mod BS), j div BS) on ORIGINAL indices:
+//    that key travels in the w component of each sorted point (j is recovered from it), so the
+//    result does not depend on the internal order.
 //  * the clouds live in L2 (20 B/point), the bucket table in shared memory; an iteration is three
-//    block barriers and one L2 round trip, and its latency is hidden by the other CTAs of the SM --
-//    a 126 MB L2 holds ~300 clouds of 24k points at once, which is what makes "one CTA per cloud,
-//    many CTAs per SM" possible on B200.
-//
-// Work drops from N point-updates per sample to roughly N*(0.001 + 0.07/sqrt(k) + 1/k) at sample k
-// for surface-like clouds (a ~16x reduction over 1024 samples of a 24k cloud).
+//    block barriers and one L2 round trip, hidden by the other CTAs of the SM -- a 126 MB L2 holds
+//    ~300 clouds of 24k points at once, which is what makes "one CTA per cloud, several CTAs per SM"
+//    possible on B200.
 #include <algorithm>
 #include <climits>
 
@@ -42,33 +43,40 @@ constexpr int kNW = kT / 32;
 constexpr int kMT = 512;           // main kernel
 constexpr int kMNW = kMT / 32;
 constexpr int kBatch = 4;          // buckets a warp keeps in flight (memory-level parallelism)
+constexpr int kMaxBuckets = 3600;   // 60 B of shared memory per bucket
 constexpr unsigned FULL = 0xffffffffu;
 
 struct BucketWs {
-    float4* pts4;     // [b][stride]   sorted (x, y, z, bits(original local index)); pads have index -1
+    float4* pts4;     // [b][stride]   sorted (x, y, z, bits(tie key)); pads carry key INT_MAX
     float* tval;      // [b][stride]   running minima in sorted order; pads -1
     uint2* key_a;     // [b][stride]   radix ping
     uint2* key_b;     // [b][stride]   radix pong
-    float4* bsphere;  // [b][nbmax]    bucket centre + inflated radius (absolute slack included)
+    float4* box_lo;   // [b][nbmax]    inflated box minimum, w = initial max t of the bucket
+    float4* box_hi;   // [b][nbmax]    inflated box maximum
     int2* bvk;        // [b][nbmax]    initial cached candidate (value bits, tie key)
-    float4* bxyzj;    // [b][nbmax]    initial cached candidate coordinates + original index
-    float* scale;     // [b]           max |coordinate| of the cloud
+    float4* bxyz;     // [b][nbmax]    initial cached candidate coordinates
     int stride, nbmax;
 };
 
 __device__ __forceinline__ int bitrev_low(int v, int bits) {
     return bits ? static_cast<int>(__brev(static_cast<unsigned>(v)) >> (32 - bits)) : 0;
 }
+// Total order of points under the reference's tie-break (smaller wins) and its inverse.
 __device__ __forceinline__ int point_key(int j, int bs_log2) {
     return (bitrev_low(j & ((1 << bs_log2) - 1), bs_log2) << 21) | (j >> bs_log2);
 }
-// Squared skip threshold of a bucket: with r' = inflated radius + absolute slack and M = max t of the
-// bucket, the bucket cannot change when D = |c - o| satisfies D > r' + sqrt(M * (1 + 1e-5)); both
-// sides are positive, so the test is D^2 > theta2 with theta2 rounded UP by the extra factors.
-__device__ __forceinline__ float skip_threshold2(float r_slack, float max_t) {
-    if (max_t < 0.f) return 0.f;                       // bucket of pads only (cannot happen)
-    const float th = (r_slack + sqrtf(max_t * 1.00002f)) * 1.000002f;
-    return th * th * 1.000002f;
+__device__ __forceinline__ int key_to_index(int key, int bs_log2) {
+    return bitrev_low(key >> 21, bs_log2) | ((key & 0x1FFFFF) << bs_log2);
+}
+// Skip threshold: a box whose squared distance to o exceeds this cannot change (rounded up).
+__device__ __forceinline__ float skip_threshold(float max_t) { return max_t < 0.f ? -1.f : max_t * 1.00002f; }
+// Squared distance from o to an axis-aligned box (0 inside).
+__device__ __forceinline__ float box_dist2(float lx, float ly, float lz, float hx, float hy, float hz, float ox, float oy,
+                                           float oz) {
+    const float ex = fmaxf(fmaxf(lx - ox, ox - hx), 0.f);
+    const float ey = fmaxf(fmaxf(ly - oy, oy - hy), 0.f);
+    const float ez = fmaxf(fmaxf(lz - oz, oz - hz), 0.f);
+    return ex * ex + ey * ey + ez * ez;
 }
 __device__ __forceinline__ unsigned spread3(unsigned x) {   // 10 bits -> every third bit
     x = (x | (x << 16)) & 0x030000FFu;
@@ -201,7 +209,7 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
         inv[a] = ext > 0.f ? 127.999f / ext : 0.f;
         scale = fmaxf(scale, fmaxf(fabsf(box[a]), fabsf(box[3 + a])));
     }
-    if (tid == 0) ws.scale[cloud] = scale;
+    const float slack = 4e-6f * scale;       // absolute inflation of every bucket box
 
     // ---- Morton keys + stable radix sort ----------------------------------------------------------------
     for (int j = tid; j < n; j += kT) {
@@ -226,37 +234,37 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
         if (p < n) {
             const int j = static_cast<int>(sorted[p].y);
             pts4[p] = make_float4(__ldg(cx + 3 * static_cast<size_t>(j)), __ldg(cx + 3 * static_cast<size_t>(j) + 1),
-                                  __ldg(cx + 3 * static_cast<size_t>(j) + 2), __int_as_float(j));
+                                  __ldg(cx + 3 * static_cast<size_t>(j) + 2), __int_as_float(point_key(j, bs_log2)));
             tval[p] = tmp ? tmp[start_n + j] : 1e10f;
         } else {
-            pts4[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            pts4[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(INT_MAX));
             tval[p] = -1.0f;
         }
     }
     __syncthreads();
 
-    // ---- bucket spheres and initial candidates ------------------------------------------------------------
+    // ---- bucket boxes and initial candidates --------------------------------------------------------------
     const int nb = npad >> 5;
-    float4* bs = ws.bsphere + static_cast<size_t>(cloud) * ws.nbmax;
+    float4* blo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
+    float4* bhi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
     int2* bvk = ws.bvk + static_cast<size_t>(cloud) * ws.nbmax;
-    float4* bxj = ws.bxyzj + static_cast<size_t>(cloud) * ws.nbmax;
+    float4* bxyz = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
     for (int bk = warp; bk < nb; bk += kNW) {
         const float4 P = pts4[bk * 32 + lane];
         const float tv = tval[bk * 32 + lane];
-        const int j = __float_as_int(P.w);
-        const bool ok = j >= 0;
+        const int key = __float_as_int(P.w);
+        const bool ok = key != INT_MAX;
         const float lx = warp_min(ok ? P.x : INFINITY), hx = warp_max(ok ? P.x : -INFINITY);
         const float ly = warp_min(ok ? P.y : INFINITY), hy = warp_max(ok ? P.y : -INFINITY);
         const float lz = warp_min(ok ? P.z : INFINITY), hz = warp_max(ok ? P.z : -INFINITY);
-        const float ccx = 0.5f * (lx + hx), ccy = 0.5f * (ly + hy), ccz = 0.5f * (lz + hz);
-        const float ddx = P.x - ccx, ddy = P.y - ccy, ddz = P.z - ccz;
-        const float r = warp_max(ok ? sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) : 0.f);
         const int bi = __float_as_int(tv);
         const int wmax = __reduce_max_sync(FULL, bi);
-        const int key = (bi == wmax && ok) ? point_key(j, bs_log2) : INT_MAX;
-        const int wkey = __reduce_min_sync(FULL, key);
-        if (lane == 0) bs[bk] = make_float4(ccx, ccy, ccz, r * 1.00001f + 4e-6f * scale);
-        if (bi == wmax && key == wkey) { bvk[bk] = make_int2(wmax, wkey); bxj[bk] = P; }
+        const int wkey = __reduce_min_sync(FULL, bi == wmax ? key : INT_MAX);
+        if (lane == 0) {
+            blo[bk] = make_float4(lx - slack, ly - slack, lz - slack, __int_as_float(wmax));
+            bhi[bk] = make_float4(hx + slack, hy + slack, hz + slack, 0.f);
+        }
+        if (bi == wmax && key == wkey) { bvk[bk] = make_int2(wmax, wkey); bxyz[bk] = P; }
     }
 }
 
@@ -266,7 +274,7 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int nact;
-    __shared__ int4 wres[kMNW];
+    __shared__ int4 wres[kMNW];           // per owner warp: (value bits, key, bucket, -)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x;
@@ -279,48 +287,77 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     if (m == 1) return;
 
     const int nb = ((n + 31) & ~31) >> 5;
-    float4* sph = reinterpret_cast<float4*>(dyn);                                   // [nbmax] centre, theta^2
-    float4* cxyzj = sph + ws.nbmax;                                                 // [nbmax] candidate x,y,z,j
-    int2* cvk = reinterpret_cast<int2*>(cxyzj + ws.nbmax);                          // [nbmax] candidate value bits, key
-    float* rad = reinterpret_cast<float*>(cvk + ws.nbmax);                          // [nbmax] inflated radius + slack
-    int* alist = reinterpret_cast<int*>(rad + ws.nbmax);                            // [nbmax] active buckets
+    float4* blo = reinterpret_cast<float4*>(dyn);                                   // [nbmax] box min, w = skip threshold
+    float4* bhi = blo + ws.nbmax;                                                   // [nbmax] box max
+    float4* cxyz = bhi + ws.nbmax;                                                  // [nbmax] candidate x,y,z,key bits
+    int2* cvk = reinterpret_cast<int2*>(cxyz + ws.nbmax);                           // [nbmax] candidate value bits, key
+    int* alist = reinterpret_cast<int*>(cvk + ws.nbmax);                            // [nbmax] active buckets
 
     const float4* pts4 = ws.pts4 + static_cast<size_t>(cloud) * ws.stride;
     float* tval = ws.tval + static_cast<size_t>(cloud) * ws.stride;
+
+    // ---- owner ranges: warp w owns buckets [r0, r1); lane l looks after r0 + l, r0 + l + 32, ... -------------
+    const int per = (nb + kMNW - 1) / kMNW;
+    const int r0 = min(nb, warp * per), r1 = min(nb, r0 + per);
     {
-        const float4* gs = ws.bsphere + static_cast<size_t>(cloud) * ws.nbmax;
+        const float4* glo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
+        const float4* ghi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
         const int2* gv = ws.bvk + static_cast<size_t>(cloud) * ws.nbmax;
-        const float4* gx = ws.bxyzj + static_cast<size_t>(cloud) * ws.nbmax;
+        const float4* gx = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
         for (int bk = tid; bk < nb; bk += kMT) {
-            const float4 c = gs[bk];
-            const int2 v = gv[bk];
-            rad[bk] = c.w;
-            sph[bk] = make_float4(c.x, c.y, c.z, skip_threshold2(c.w, __int_as_float(v.x)));
-            cvk[bk] = v;
-            cxyzj[bk] = gx[bk];
+            float4 lo = glo[bk];
+            lo.w = skip_threshold(lo.w);                     // w held the bucket's initial max t
+            blo[bk] = lo; bhi[bk] = ghi[bk]; cvk[bk] = gv[bk]; cxyz[bk] = gx[bk];
         }
         if (tid == 0) nact = 0;
     }
+    __syncthreads();
+    // union box of the range (registers, fixed) and the range candidate
+    float ulx = INFINITY, uly = INFINITY, ulz = INFINITY, uhx = -INFINITY, uhy = -INFINITY, uhz = -INFINITY;
+    for (int bk = r0 + lane; bk < r1; bk += 32) {
+        const float4 lo = blo[bk], hi = bhi[bk];
+        ulx = fminf(ulx, lo.x); uly = fminf(uly, lo.y); ulz = fminf(ulz, lo.z);
+        uhx = fmaxf(uhx, hi.x); uhy = fmaxf(uhy, hi.y); uhz = fmaxf(uhz, hi.z);
+    }
+    ulx = warp_min(ulx); uly = warp_min(uly); ulz = warp_min(ulz);
+    uhx = warp_max(uhx); uhy = warp_max(uhy); uhz = warp_max(uhz);
+
+    auto refresh_range = [&]() {          // best candidate over the owned buckets -> wres[warp]
+        int bv = INT_MIN, bkey = INT_MAX, bbk = r0;
+        for (int bk = r0 + lane; bk < r1; bk += 32) {
+            const int2 c = cvk[bk];
+            if (c.x > bv || (c.x == bv && c.y < bkey)) { bv = c.x; bkey = c.y; bbk = bk; }
+        }
+        const int wv = __reduce_max_sync(FULL, bv);
+        const int wk = __reduce_min_sync(FULL, bv == wv ? bkey : INT_MAX);
+        if (bv == wv && bkey == wk) wres[warp] = make_int4(wv, wk, bbk, 0);
+        return wv;
+    };
+    float range_thr = skip_threshold(__int_as_float(refresh_range()));     // r0 == r1: INT_MIN -> negative -> -1
+
     float ox = __ldg(xyz + 3 * static_cast<size_t>(start_n)), oy = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 1),
           oz = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 2);
     __syncthreads();
 
-    const int nb_round = (nb + kMT - 1) / kMT * kMT;
     for (int it = 1; it < m; ++it) {
-        // ---- (a) which buckets can change? --------------------------------------------------------------
-        for (int bk = tid; bk < nb_round; bk += kMT) {
-            bool act = false;
-            if (bk < nb) {
-                const float4 c = sph[bk];
-                const float dx = c.x - ox, dy = c.y - oy, dz = c.z - oz;
-                act = !(dx * dx + dy * dy + dz * dz > c.w);        // D^2 > theta^2  ->  nothing can change
-            }
-            const unsigned mask = __ballot_sync(FULL, act);
-            if (mask) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&nact, __popc(mask));
-                base = __shfl_sync(FULL, base, 0);
-                if (act) alist[base + __popc(mask & ((1u << lane) - 1u))] = bk;
+        // ---- (a) owner warps: can anything in my range change?  which buckets? ------------------------------
+        bool dirty = false;
+        if (r0 < r1 && !(box_dist2(ulx, uly, ulz, uhx, uhy, uhz, ox, oy, oz) > range_thr)) {
+            for (int base = r0; base < r1; base += 32) {
+                const int bk = base + lane;
+                bool act = false;
+                if (bk < r1) {
+                    const float4 lo = blo[bk], hi = bhi[bk];
+                    act = !(box_dist2(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, ox, oy, oz) > lo.w);
+                }
+                const unsigned mask = __ballot_sync(FULL, act);
+                if (mask) {
+                    dirty = true;
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(&nact, __popc(mask));
+                    pos = __shfl_sync(FULL, pos, 0);
+                    if (act) alist[pos + __popc(mask & ((1u << lane) - 1u))] = bk;
+                }
             }
         }
         __syncthreads();
@@ -351,30 +388,19 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
                 if (nt < tv[u]) __stcg(tval + bk[u] * 32 + lane, nt);
                 const int bi = __float_as_int(nt);          // pads stay at -1
                 const int wmax = __reduce_max_sync(FULL, bi);
-                const int key = (bi == wmax) ? point_key(__float_as_int(P[u].w), bs_log2) : INT_MAX;
-                const int wkey = __reduce_min_sync(FULL, key);
-                if (bi == wmax && key == wkey) {
+                const int wkey = __reduce_min_sync(FULL, bi == wmax ? __float_as_int(P[u].w) : INT_MAX);
+                if (bi == wmax && __float_as_int(P[u].w) == wkey) {
                     cvk[bk[u]] = make_int2(wmax, wkey);
-                    cxyzj[bk[u]] = P[u];
-                    const float4 c = sph[bk[u]];
-                    sph[bk[u]] = make_float4(c.x, c.y, c.z, skip_threshold2(rad[bk[u]], nt));
+                    cxyz[bk[u]] = P[u];
+                    blo[bk[u]].w = skip_threshold(nt);
                 }
             }
         }
         __syncthreads();
         if (tid == 0) nact = 0;
 
-        // ---- (c) arg-max over the cached candidates of all buckets -----------------------------------------
-        int bv = INT_MIN, bkey = INT_MAX, bbk = 0;
-        for (int b2 = tid; b2 < nb; b2 += kMT) {
-            const int2 c = cvk[b2];
-            if (c.x > bv || (c.x == bv && c.y < bkey)) { bv = c.x; bkey = c.y; bbk = b2; }
-        }
-        {
-            const int wv = __reduce_max_sync(FULL, bv);
-            const int wk = __reduce_min_sync(FULL, bv == wv ? bkey : INT_MAX);
-            if (bv == wv && bkey == wk) wres[warp] = make_int4(wv, wk, bbk, 0);
-        }
+        // ---- (c) touched ranges refresh their candidate; block arg-max over the 16 range candidates ------------
+        if (dirty) range_thr = skip_threshold(__int_as_float(refresh_range()));
         __syncthreads();
         {
             int4 c = make_int4(INT_MIN, INT_MAX, 0, 0);
@@ -383,16 +409,16 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
             const int gk = __reduce_min_sync(FULL, c.x == gv ? c.y : INT_MAX);
             const int src = __ffs(__ballot_sync(FULL, c.x == gv && c.y == gk)) - 1;
             const int bstar = __shfl_sync(FULL, c.z, src);
-            const float4 w = cxyzj[bstar];
+            const float4 w = cxyz[bstar];
             ox = w.x; oy = w.y; oz = w.z;
-            if (tid == 0) idx[start_m + it] = start_n + __float_as_int(w.w);
+            if (tid == 0) idx[start_m + it] = start_n + key_to_index(__float_as_int(w.w), bs_log2);
         }
     }
 
     if (tmp) {
         __syncthreads();
         for (int p = tid; p < n; p += kMT) {
-            const int j = __float_as_int(__ldg(&pts4[p].w));
+            const int j = key_to_index(__float_as_int(__ldg(&pts4[p].w)), bs_log2);
             tmp[start_n + j] = __ldcg(tval + p);
         }
     }
@@ -402,8 +428,8 @@ bool g_pool_configured = false;
 
 }  // namespace
 
-// Largest cloud the bucket kernel takes (bucket table in shared memory: 48 bytes per 32 points).
-int fps_bucket_max_points() { return 4096 * 32; }
+// Largest cloud the bucket kernel takes (the bucket table must fit in shared memory).
+int fps_bucket_max_points() { return kMaxBuckets * 32; }
 
 int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
                       int bs_log2, cudaStream_t stream)
@@ -417,8 +443,8 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     size_t off = 0;
     auto take = [&off](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~static_cast<size_t>(255); return o; };
     const size_t o_pts = take(pts * sizeof(float4)), o_t = take(pts * sizeof(float)), o_ka = take(pts * sizeof(uint2)),
-                 o_kb = take(pts * sizeof(uint2)), o_bs = take(nbt * sizeof(float4)), o_bv = take(nbt * sizeof(int2)),
-                 o_bx = take(nbt * sizeof(float4)), o_sc = take(static_cast<size_t>(b) * sizeof(float));
+                 o_kb = take(pts * sizeof(uint2)), o_lo = take(nbt * sizeof(float4)), o_hi = take(nbt * sizeof(float4)),
+                 o_bv = take(nbt * sizeof(int2)), o_bx = take(nbt * sizeof(float4));
     if (!g_pool_configured) {            // keep freed blocks in the pool instead of returning them to the OS
         int dev = 0;
         cudaMemPool_t pool;
@@ -436,15 +462,15 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     ws.tval = reinterpret_cast<float*>(base + o_t);
     ws.key_a = reinterpret_cast<uint2*>(base + o_ka);
     ws.key_b = reinterpret_cast<uint2*>(base + o_kb);
-    ws.bsphere = reinterpret_cast<float4*>(base + o_bs);
+    ws.box_lo = reinterpret_cast<float4*>(base + o_lo);
+    ws.box_hi = reinterpret_cast<float4*>(base + o_hi);
     ws.bvk = reinterpret_cast<int2*>(base + o_bv);
-    ws.bxyzj = reinterpret_cast<float4*>(base + o_bx);
-    ws.scale = reinterpret_cast<float*>(base + o_sc);
+    ws.bxyz = reinterpret_cast<float4*>(base + o_bx);
 
     fps_bucket_sort_kernel<<<b, kT, 0, stream>>>(xyz, offset, tmp, ws, bs_log2);
     int rc = check_launch("fps_bucket_sort_kernel");
     if (rc == TGN_OK) {
-        const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 2 + sizeof(int2) + sizeof(float) + sizeof(int));
+        const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 3 + sizeof(int2) + sizeof(int));
         static size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
             e = cudaFuncSetAttribute(fps_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
