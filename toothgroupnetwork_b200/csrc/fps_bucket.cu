@@ -43,6 +43,7 @@ constexpr int kNW = kT / 32;
 constexpr int kMT = 512;           // main kernel
 constexpr int kMNW = kMT / 32;
 constexpr int kBatch = 4;          // buckets a warp keeps in flight (memory-level parallelism)
+constexpr int kRadixUnroll = 4;    // radix steps whose loads are issued together
 constexpr int kMaxBuckets = 3600;   // 60 B of shared memory per bucket
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -106,12 +107,22 @@ __device__ void radix_pass7(const uint2* __restrict__ src, uint2* __restrict__ d
     const int lo = warp * per_warp, hi = min(n, lo + per_warp);
     for (int i = tid; i < kNW * 128; i += kT) (&hist[0][0])[i] = 0;
     __syncthreads();
-    for (int base = lo; base < hi; base += 32) {
-        const int i = base + lane;
-        const bool ok = i < hi;
-        const int d = ok ? static_cast<int>((src[i].x >> shift) & 127u) : 128 + lane;   // unique dummy digits
-        const unsigned m = __match_any_sync(FULL, d);
-        if (ok && lane == __ffs(m) - 1) hist[warp][d] += __popc(m);
+    for (int base = lo; base < hi; base += 32 * kRadixUnroll) {
+        unsigned code[kRadixUnroll];
+#pragma unroll
+        for (int u = 0; u < kRadixUnroll; ++u) {          // independent loads first (L2 latency paid once)
+            const int i = base + 32 * u + lane;
+            code[u] = i < hi ? src[i].x : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kRadixUnroll; ++u) {
+            const int i = base + 32 * u + lane;
+            const bool ok = i < hi;
+            const int d = ok ? static_cast<int>((code[u] >> shift) & 127u) : 128 + lane;   // unique dummy digits
+            const unsigned m = __match_any_sync(FULL, d);
+            if (ok && lane == __ffs(m) - 1) hist[warp][d] += __popc(m);
+            __syncwarp();
+        }
     }
     __syncthreads();
     // digit-major, warp-minor exclusive scan
@@ -141,22 +152,29 @@ __device__ void radix_pass7(const uint2* __restrict__ src, uint2* __restrict__ d
         for (int w = 0; w < kNW; ++w) { const int c = hist[w][tid]; hist[w][tid] = run; run += c; }
     }
     __syncthreads();
-    for (int base = lo; base < hi; base += 32) {
-        const int i = base + lane;
-        const bool ok = i < hi;
-        uint2 e = make_uint2(0u, 0u);
-        if (ok) e = src[i];
-        const int d = ok ? static_cast<int>((e.x >> shift) & 127u) : 128 + lane;
-        const unsigned m = __match_any_sync(FULL, d);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        int cur = 0;
-        if (ok) cur = hist[warp][d];
-        __syncwarp();
-        if (ok) {
-            dst[cur + rank] = e;
-            if (lane == __ffs(m) - 1) hist[warp][d] = cur + __popc(m);
+    for (int base = lo; base < hi; base += 32 * kRadixUnroll) {
+        uint2 el[kRadixUnroll];
+#pragma unroll
+        for (int u = 0; u < kRadixUnroll; ++u) {
+            const int i = base + 32 * u + lane;
+            el[u] = i < hi ? src[i] : make_uint2(0u, 0u);
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kRadixUnroll; ++u) {
+            const int i = base + 32 * u + lane;
+            const bool ok = i < hi;
+            const int d = ok ? static_cast<int>((el[u].x >> shift) & 127u) : 128 + lane;
+            const unsigned m = __match_any_sync(FULL, d);
+            const int rank = __popc(m & ((1u << lane) - 1u));
+            int cur = 0;
+            if (ok) cur = hist[warp][d];
+            __syncwarp();
+            if (ok) {
+                dst[cur + rank] = el[u];
+                if (lane == __ffs(m) - 1) hist[warp][d] = cur + __popc(m);
+            }
+            __syncwarp();
+        }
     }
     __syncthreads();
 }
@@ -268,7 +286,7 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
     }
 }
 
-__global__ void __launch_bounds__(kMT)
+__global__ void __launch_bounds__(kMT, 2)      // <= 64 registers: two clouds per SM hide each other's barriers
 fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                   float* tmp, int* __restrict__ idx, BucketWs ws, int bs_log2)
 {
