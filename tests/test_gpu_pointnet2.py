@@ -317,6 +317,12 @@ def test_state_dict_keys_match_reference_layout():
     assert "mlp_convs.0.weight" in fp.state_dict() and fp.state_dict()["mlp_convs.0.weight"].dim() == 3
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 1000), (2, 1000, 3), (2, 6, 24000), (1, 24000, 6), (3, 40, 70), (1, 8, 300), (2, 1, 5)])
+def test_transpose_kernels(shape):
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(0)).cuda()
+    assert torch.equal(pn2.transpose_last2(x), x.permute(0, 2, 1).contiguous())
+
+
 def test_farthest_point_sample_wrapper_and_index_points():
     xyz = torch.stack([clouds.cube(5000, 1), clouds.cube(5000, 2)]).cuda()
     idx = pn2.farthest_point_sample(xyz, 256)

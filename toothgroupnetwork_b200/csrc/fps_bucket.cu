@@ -286,10 +286,15 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
     }
 }
 
-__global__ void __launch_bounds__(kMT, 2)      // <= 64 registers: two clouds per SM hide each other's barriers
+// MT_ = 512: 16 warps per cloud, 2 clouds per SM (shortest iteration; batches up to 2 clouds per SM).
+// MT_ = 256:  8 warps per cloud, 4 clouds per SM (more clouds in flight hide the barriers of large batches).
+// Either way <= 64 registers per thread.
+template <int MT_>
+__global__ void __launch_bounds__(MT_, 1024 / MT_)
 fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                   float* tmp, int* __restrict__ idx, BucketWs ws, int bs_log2)
 {
+    constexpr int kMT = MT_, kMNW = MT_ / 32;     // shadow the defaults
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int nact;
     __shared__ int4 wres[kMNW];           // per owner warp: (value bits, key, bucket, -)
@@ -489,14 +494,19 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     int rc = check_launch("fps_bucket_sort_kernel");
     if (rc == TGN_OK) {
         const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 3 + sizeof(int2) + sizeof(int));
-        static size_t configured = 0;
+        // more than two clouds per SM: narrower CTAs, four clouds per SM in flight
+        const bool narrow = b > 2 * sm_count() && 4 * smem <= 200 * 1024;
+        static size_t configured_wide = 0, configured_narrow = 0;
+        size_t& configured = narrow ? configured_narrow : configured_wide;
         if (smem > 48 * 1024 && smem > configured) {
-            e = cudaFuncSetAttribute(fps_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            e = narrow ? cudaFuncSetAttribute(fps_bucket_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                       : cudaFuncSetAttribute(fps_bucket_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = TGN_ERR_CUDA; }
             else configured = smem;
         }
         if (rc == TGN_OK) {
-            fps_bucket_kernel<<<b, kMT, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
+            if (narrow) fps_bucket_kernel<256><<<b, 256, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
+            else fps_bucket_kernel<512><<<b, 512, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
             rc = check_launch("fps_bucket_kernel");
         }
     }

@@ -223,6 +223,42 @@ transpose_kernel(int R, int C, const float* __restrict__ in, float* __restrict__
     }
 }
 
+// Same transpose when one side is tiny (xyz: 3, xyz+normals: 6 ...): a 32x32 tile would be mostly
+// padding.  One thread per long-axis index; the long axis is the coalesced one on both sides
+// (reads of a short row are contiguous per thread and contiguous across neighbouring threads).
+template <int MAXS>
+__global__ void __launch_bounds__(256)
+transpose_short_rows_kernel(int R, int C, const float* __restrict__ in, float* __restrict__ out)
+{   // in (R, C) with R <= MAXS short, C long  ->  out (C, R)
+    const int b = blockIdx.y;
+    const float* ib = in + static_cast<size_t>(b) * R * C;
+    float* ob = out + static_cast<size_t>(b) * R * C;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        float v[MAXS];
+#pragma unroll
+        for (int r = 0; r < MAXS; ++r) v[r] = r < R ? __ldg(ib + static_cast<size_t>(r) * C + c) : 0.f;
+#pragma unroll
+        for (int r = 0; r < MAXS; ++r)
+            if (r < R) ob[static_cast<size_t>(c) * R + r] = v[r];
+    }
+}
+template <int MAXS>
+__global__ void __launch_bounds__(256)
+transpose_short_cols_kernel(int R, int C, const float* __restrict__ in, float* __restrict__ out)
+{   // in (R, C) with R long, C <= MAXS short  ->  out (C, R)
+    const int b = blockIdx.y;
+    const float* ib = in + static_cast<size_t>(b) * R * C;
+    float* ob = out + static_cast<size_t>(b) * R * C;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+        float v[MAXS];
+#pragma unroll
+        for (int c = 0; c < MAXS; ++c) v[c] = c < C ? __ldg(ib + static_cast<size_t>(r) * C + c) : 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXS; ++c)
+            if (c < C) ob[static_cast<size_t>(c) * R + r] = v[c];
+    }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -323,6 +359,17 @@ int tgn_transpose_cn(int B, int C, int N, const float* in, float* out, void* str
     // in (B, C, N) -> out (B, N, C): rows R = C, cols = N in the kernel's naming
     if (B <= 0 || C <= 0 || N <= 0) return TGN_OK;
     if (B > 65535 || (C + 31) / 32 > 65535) { set_error("transpose: shape exceeds grid limits"); return TGN_ERR_INVALID; }
+    // in (B, C rows, N cols): rows = C, cols = N in the kernels' naming
+    if (C <= 8 && N >= 256) {
+        dim3 g(std::min((N + 255) / 256, 4 * sm_count()), B);
+        transpose_short_rows_kernel<8><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, N, in, out);
+        return check_launch("transpose_short_rows_kernel");
+    }
+    if (N <= 8 && C >= 256) {
+        dim3 g(std::min((C + 255) / 256, 4 * sm_count()), B);
+        transpose_short_cols_kernel<8><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, N, in, out);
+        return check_launch("transpose_short_cols_kernel");
+    }
     dim3 grid((N + 31) / 32, (C + 31) / 32, B);
     transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, N, in, out);
     return check_launch("transpose_kernel");
