@@ -18,7 +18,7 @@ metric = sampled points per second = clouds * 1024 / time, whole job (all ranks)
   CUDA-event time inside the timed region, against the measured HBM copy peak.
 * ``cpu_baseline`` / ``--impl reference``: the oracle's port of the reference's CPU-capable
   formulation of the same path, timed on the host cores on a bounded sample of the workload.
-Inputs are larger than L2 (B*24000*6*4 bytes > 126 MB for B >= 230); no explicit flush.
+Inputs are larger than L2 (B*24000*6*4 bytes = 341 MB at the default B = 592); no explicit flush.
 """
 from __future__ import annotations
 
@@ -40,6 +40,21 @@ MLP = [32, 32, 64]
 METRIC = "sampled-points/sec (FPS+ballq+group-MLP, 24k-pt cloud)"
 UNIT = "sampled points/s"
 WORKLOAD = "pointnet++ SA1 forward: FPS 24000->1024, ball query r=0.1 K=32, group-MLP 9->[32,32,64], eval BN"
+
+
+def host_cores() -> int:
+    """Host threads this process may actually use (cgroup / affinity aware), not the machine total."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:   # cgroup v2 CPU quota
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 def measured_peaks():
@@ -156,7 +171,7 @@ def cpu_layers_of(sa):
 
 
 def time_cpu(sa, sample_clouds: int, steps: int, warmup: int):
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     feats = make_clouds(0, sample_clouds)
     layers = cpu_layers_of(sa)
@@ -176,7 +191,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clouds", type=int, default=296, help="clouds per GPU per step")
+    ap.add_argument("--clouds", type=int, default=592, help="clouds per GPU per step (4 per SM)")
     ap.add_argument("--cpu-clouds", type=int, default=0, help="clouds in the CPU sample (default: host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fps-mode", type=int, default=0, help="0 auto; 100*G+CS forces an FPS kernel shape (experiments)")
@@ -195,7 +210,7 @@ def main():
         if rank != 0:
             return
         sa = build_module("cpu")
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         sample = args.cpu_clouds or cores
         value, dt, cores = time_cpu(sa, sample, max(1, args.steps), max(0, args.warmup))
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -320,7 +335,7 @@ def main():
         "parity_ok": bool(agg["parity_ok"]),
     }
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         sample = args.cpu_clouds or cores
         cv, cdt, cores = time_cpu(sa.cpu(), sample, 2, 1)
         line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",

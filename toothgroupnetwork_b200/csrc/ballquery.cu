@@ -45,6 +45,15 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ pts, int ba
                     z = __ldg(pts + 3 * static_cast<size_t>(base + i) + 2);
         sx[i] = x; sy[i] = y; sz[i] = z; sn[i] = sq_norm_unfused(x, y, z);
     }
+    // pad to a multiple of 128 with points at infinite distance (never a member, never a neighbour)
+    for (int i = cnt + threadIdx.x; i < ((cnt + 127) & ~127); i += THREADS) {
+        sx[i] = 0.f; sy[i] = 0.f; sz[i] = 0.f; sn[i] = INFINITY;
+    }
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
 // One warp per query, WARPS queries of one cloud per CTA.  Lanes test 32 consecutive points per
@@ -71,22 +80,33 @@ ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__
     }
     int cnt = live ? 0 : nsample;     // dead warps count as finished
     int first = N;                    // sentinel the reference leaves when the ball is empty
+    const uint32_t a_x = smem_u32(sx), a_y = smem_u32(sy), a_z = smem_u32(sz), a_n = smem_u32(sn);
     for (int base = 0; base < N; base += kTile) {
         const int tile = min(kTile, N - base);
         __syncthreads();              // previous tile fully consumed
         stage_tile<WARPS * 32>(pts, base, tile, sx, sy, sz, sn);
         __syncthreads();
         if (cnt < nsample) {
-            for (int o = 0; o < tile && cnt < nsample; o += 32) {
-                const int i = o + lane;
-                bool hit = false;
-                if (i < tile) hit = !(sq_dist_expanded(ax, ay, az, an, sx[i], sy[i], sz[i], sn[i]) > r2);
-                const unsigned mask = __ballot_sync(FULL, hit);
-                if (mask) {
-                    if (cnt == 0) first = base + o + __ffs(mask) - 1;
-                    const int pos = cnt + __popc(mask & ((1u << lane) - 1));
-                    if (hit && pos < nsample) row[pos] = static_cast<IdxT>(base + i);
-                    cnt += __popc(mask);
+            // four 32-point steps per trip: 16 shared loads issued together, one early-exit test per 128
+            // points (the tile arrays are padded to a multiple of 128 with points that can never hit)
+            for (int o = 0; o < tile && cnt < nsample; o += 128) {
+                float d[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t off = static_cast<uint32_t>(o + 32 * u + lane) * 4u;
+                    d[u] = sq_dist_expanded(ax, ay, az, an, lds_f32(a_x + off), lds_f32(a_y + off), lds_f32(a_z + off),
+                                            lds_f32(a_n + off));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool hit = !(d[u] > r2);
+                    const unsigned mask = __ballot_sync(FULL, hit);
+                    if (mask) {
+                        if (cnt == 0) first = base + o + 32 * u + __ffs(mask) - 1;
+                        const int pos = cnt + __popc(mask & ((1u << lane) - 1));
+                        if (hit && pos < nsample) row[pos] = static_cast<IdxT>(base + o + 32 * u + lane);
+                        cnt += __popc(mask);
+                    }
                 }
             }
         }
