@@ -157,13 +157,50 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
     float* part = reinterpret_cast<float*>(smem + lay.part[g]);
     const uint64_t desc_a_hi = make_smem_desc(a_hi, kChunkStrideA, 128);
     const uint64_t desc_a_lo = make_smem_desc(a_lo, kChunkStrideA, 128);
-    int j_next = -1;
+    const int xoff = p.xyz_first ? 0 : p.D;       // first channel of the xyz_rel block
+    const int foff = p.xyz_first ? 3 : 0;         // first channel of the feature block
+    // neighbour index of this thread's row in tile `t` (-1 past the end / past the rows of the tile)
+    auto load_index = [&](int t) -> int {
+        if (t >= total_tiles) return -1;
+        const int tb = t / lay.tiles_per_cloud;
+        const int ts0 = (t - tb * lay.tiles_per_cloud) * lay.gpt;
+        if (r >= min(lay.gpt, p.S - ts0) * p.K) return -1;
+        return __ldg(p.gidx + (static_cast<size_t>(tb) * p.S + ts0) * p.K + r);
+    };
+    // the 16-wide zero-padded [xyz_rel | feats] (or [feats | xyz_rel]) row of this thread in tile `t`
+    auto load_row16 = [&](int t, int j, float (&out)[16]) {
+        const bool ok = t < total_tiles && j >= 0 && j < p.N;
+        const int tb = ok ? t / lay.tiles_per_cloud : 0;
+        const int ts = ok ? (t - tb * lay.tiles_per_cloud) * lay.gpt + r / p.K : 0;
+        const int jj = ok ? j : 0;
+        const float* px = p.xyz + 3 * (static_cast<size_t>(tb) * p.N + jj);
+        const float* pc = p.new_xyz + 3 * (static_cast<size_t>(tb) * p.S + ts);
+        const float* pf = p.feats ? p.feats + (static_cast<size_t>(tb) * p.N + jj) * p.D : px;
+        const float rel0 = __fsub_rn(__ldg(px), __ldg(pc)), rel1 = __fsub_rn(__ldg(px + 1), __ldg(pc + 1)),
+                    rel2 = __fsub_rn(__ldg(px + 2), __ldg(pc + 2));
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int xc = c - xoff;
+            float v = xc == 0 ? rel0 : (xc == 1 ? rel1 : rel2);
+            if (static_cast<unsigned>(xc) > 2u) {
+                const unsigned fc = static_cast<unsigned>(c - foff);
+                v = fc < static_cast<unsigned>(p.D) ? __ldg(pf + fc) : 0.f;
+            }
+            out[c] = ok ? v : 0.f;
+        }
+    };
+    const bool fast_rows = lay.kpad[0] == 16;     // the whole padded input row fits 16 registers
+    float row[16];
+    int j_next;
     {
         const int t0 = blockIdx.x * kGroups + g;
-        if (t0 < total_tiles) {
-            const int b0 = t0 / lay.tiles_per_cloud;
-            const int s00 = (t0 - b0 * lay.tiles_per_cloud) * lay.gpt;
-            if (r < min(lay.gpt, p.S - s00) * p.K) j_next = __ldg(p.gidx + (static_cast<size_t>(b0) * p.S + s00) * p.K + r);
+        if (fast_rows) {
+            load_row16(t0, load_index(t0), row);
+            j_next = load_index(t0 + tile_step);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) row[c] = 0.f;
+            j_next = load_index(t0);
         }
     }
 
@@ -174,7 +211,20 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
         const int rows = groups * p.K;
 
         // ---- layer-0 operand: this thread's grouped row --------------------------------------------
-        {
+        if (fast_rows) {
+            // the 16-wide padded row was loaded into registers while the previous tile computed
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32(row[4 * kc + i], hi[i], lo[i]);
+                const uint32_t off = kc * kChunkStrideA + r * 16;
+                st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+            }
+            load_row16(tile + tile_step, j_next, row);          // consumed one tile later: latency hidden
+            j_next = load_index(tile + 2 * tile_step);
+        } else {
             int j = j_next;                               // index prefetched while the previous tile computed
             const int s = s0 + (r < rows ? r / p.K : 0);
             if (r >= rows || j < 0 || j >= p.N) j = -1;
@@ -184,8 +234,6 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             const float* pf = p.feats ? p.feats + (static_cast<size_t>(b) * p.N + jj) * p.D : px;
             const float rel0 = __fsub_rn(__ldg(px), __ldg(pc)), rel1 = __fsub_rn(__ldg(px + 1), __ldg(pc + 1)),
                         rel2 = __fsub_rn(__ldg(px + 2), __ldg(pc + 2));
-            const int xoff = p.xyz_first ? 0 : p.D;       // first channel of the xyz_rel block
-            const int foff = p.xyz_first ? 3 : 0;         // first channel of the feature block
             for (int kc = 0; kc < lay.kpad[0] / 4; ++kc) {
                 uint32_t hi[4], lo[4];
 #pragma unroll
@@ -204,14 +252,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                 st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
                 st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
             }
-            // prefetch the neighbour index of this thread's row in the group's next tile
-            const int nt = tile + tile_step;
-            j_next = -1;
-            if (nt < total_tiles) {
-                const int nb = nt / lay.tiles_per_cloud;
-                const int ns0 = (nt - nb * lay.tiles_per_cloud) * lay.gpt;
-                if (r < min(lay.gpt, p.S - ns0) * p.K) j_next = __ldg(p.gidx + (static_cast<size_t>(nb) * p.S + ns0) * p.K + r);
-            }
+            j_next = load_index(tile + tile_step);
         }
 
         for (int l = 0; l < p.L; ++l) {
@@ -219,10 +260,11 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             proxy_fence_async();           // this thread's operand stores -> visible to the tensor core
             tc_fence_before();
             group_sync(g);
-            if (r == 0) {
+            if ((warp & 3) == 0) {
+                // The whole first warp of the group runs the issue code (warp-uniform descriptor maths
+                // stays on the uniform datapath); one lane issues.  The start-address field is the low
+                // 14 bits (units of 16 B): a K-step advances it by a constant.
                 tc_fence_after();
-                // The start-address field is the low 14 bits (units of 16 B): a K-step advances it by a
-                // constant, so the descriptors are built once per layer and bumped by an add.
                 const uint32_t idesc = make_idesc_tf32(np);
                 const uint32_t lbo_b = static_cast<uint32_t>(np) * 16;
                 uint64_t d_ahi = desc_a_hi, d_alo = desc_a_lo;
@@ -231,12 +273,15 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                 const uint64_t step_a = (2 * kChunkStrideA) >> 4, step_b = (2 * lbo_b) >> 4;
                 const int nks = kp / 8;
                 for (int ks = 0; ks < nks; ++ks) {
-                    mma_tf32_ss(tmem_base, d_ahi, d_bhi, idesc, ks > 0);
-                    mma_tf32_ss(tmem_base, d_alo, d_bhi, idesc, true);
-                    mma_tf32_ss(tmem_base, d_ahi, d_blo, idesc, true);
+                    if (lane == 0) {
+                        mma_tf32_ss(tmem_base, d_ahi, d_bhi, idesc, ks > 0);
+                        mma_tf32_ss(tmem_base, d_alo, d_bhi, idesc, true);
+                        mma_tf32_ss(tmem_base, d_ahi, d_blo, idesc, true);
+                    }
                     d_ahi += step_a; d_alo += step_a; d_bhi += step_b; d_blo += step_b;
                 }
-                mma_commit(bar);           // arrives on the group's mbarrier when the MMAs above have completed
+                if (lane == 0) mma_commit(bar);   // arrives on the group's mbarrier when the MMAs above have completed
+                __syncwarp();
             }
             mbar_wait_relaxed(bar, phase);
             phase ^= 1;
