@@ -43,6 +43,7 @@ struct TcLayout {
     uint32_t w_hi[kSaMaxLayers], w_lo[kSaMaxLayers], bias[kSaMaxLayers];   // byte offsets in dynamic smem
     uint32_t a_hi[kGroups], a_lo[kGroups];   // per group A operands; a_hi doubles as fp32 staging for generic K
     uint32_t part[kGroups];          // per group: up to 8 per-warp partial maxima rows of npad floats
+    uint32_t ones;                   // constant [128 x 8] A tile that adds the bias through the MMA
     uint32_t misc;                   // tmem base (u32) @0, group mbarriers (u64) @8+8g
     uint32_t total;
     uint32_t tmem_cols, group_cols;
@@ -137,8 +138,21 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             *reinterpret_cast<uint32_t*>(smem + lay.w_hi[l] + off) = hi;
             *reinterpret_cast<uint32_t*>(smem + lay.w_lo[l] + off) = lo;
         }
-        float* bs = reinterpret_cast<float*>(smem + lay.bias[l]);
-        for (int n = tid; n < np; n += kThreads) bs[n] = n < cout ? __ldg(p.bias[l] + n) : 0.f;
+        // bias as a B operand of one extra K=8 step: column k=0 holds bias_hi, k=1 bias_lo (rest 0);
+        // multiplied by the constant "ones" A tile below it adds bias_hi + bias_lo to every row.
+        for (int e = tid; e < np * 8; e += kThreads) {
+            const int n = e >> 3, k = e & 7;
+            uint32_t hi = 0u, lo = 0u;
+            if (n < cout) split_tf32(__ldg(p.bias[l] + n), hi, lo);
+            const uint32_t off = static_cast<uint32_t>(k >> 2) * (np * 16) + n * 16 + (k & 3) * 4;
+            *reinterpret_cast<uint32_t*>(smem + lay.bias[l] + off) = k == 0 ? hi : (k == 1 ? lo : 0u);
+        }
+    }
+    // constant A tile [128 rows x 8]: columns 0 and 1 are 1.0 (exact in tf32), the rest 0
+    for (int e = tid; e < kRows * 8; e += kThreads) {
+        const int rr = e >> 3, k = e & 7;
+        *reinterpret_cast<float*>(smem + lay.ones + static_cast<uint32_t>(k >> 2) * kChunkStrideA + rr * 16 + (k & 3) * 4) =
+            k < 2 ? 1.0f : 0.0f;
     }
     proxy_fence_async();
     tc_fence_before();
@@ -280,14 +294,17 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                     }
                     d_ahi += step_a; d_alo += step_a; d_bhi += step_b; d_blo += step_b;
                 }
-                if (lane == 0) mma_commit(bar);   // arrives on the group's mbarrier when the MMAs above have completed
+                if (lane == 0) {
+                    mma_tf32_ss(tmem_base, make_smem_desc(sbase + lay.ones, kChunkStrideA, 128),
+                                make_smem_desc(sbase + lay.bias[l], lbo_b, 128), idesc, true);     // + bias
+                    mma_commit(bar);       // arrives on the group's mbarrier when the MMAs above have completed
+                }
                 __syncwarp();
             }
             mbar_wait_relaxed(bar, phase);
             phase ^= 1;
             tc_fence_after();
 
-            const float* bs = reinterpret_cast<const float*>(smem + lay.bias[l]);
             const bool last = (l == p.L - 1);
             for (int c0 = 0; c0 < np; c0 += 32) {
                 uint32_t v[32];
@@ -301,7 +318,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
-                                split_tf32(fmaxf(__uint_as_float(v[i + u]) + bs[c0 + i + u], 0.f), hi[u], lo[u]);
+                                split_tf32(fmaxf(__uint_as_float(v[i + u]), 0.f), hi[u], lo[u]);
                             const uint32_t off = static_cast<uint32_t>((c0 + i) >> 2) * kChunkStrideA + r * 16;
                             st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
                             st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
@@ -318,7 +335,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             if (i < 16 || full) {
-                                const float x = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f) * live;
+                                const float x = fmaxf(__uint_as_float(v[i]), 0.f) * live;
                                 const int mx = __reduce_max_sync(FULL, __float_as_int(x));
                                 if (lane == 0) dst[i] = __int_as_float(mx);
                             }
@@ -329,7 +346,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             if (i < 16 || full) {
-                                const float x = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f) * live;
+                                const float x = fmaxf(__uint_as_float(v[i]), 0.f) * live;
                                 const int ma = __reduce_max_sync(FULL, lane < 16 ? __float_as_int(x) : 0);
                                 const int mb = __reduce_max_sync(FULL, lane >= 16 ? __float_as_int(x) : 0);
                                 if (lane == 0) { da[i] = __int_as_float(ma); db[i] = __int_as_float(mb); }
@@ -341,7 +358,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (i < 16 || full)
-                            stage[r * lay.stage_stride + c0 + i] = fmaxf(__uint_as_float(v[i]) + bs[c0 + i], 0.f);
+                            stage[r * lay.stage_stride + c0 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
                 }
             }
             tc_fence_before();             // TMEM reads done before the next layer's MMAs overwrite D
@@ -413,8 +430,9 @@ bool make_layout(const SaParams& p, TcLayout& lay)
         const uint32_t wb = static_cast<uint32_t>(lay.npad[l]) * lay.kpad[l] * 4;
         lay.w_hi[l] = take(wb, 128);
         lay.w_lo[l] = take(wb, 128);
-        lay.bias[l] = take(lay.npad[l] * 4, 16);
+        lay.bias[l] = take(lay.npad[l] * 32, 128);       // [npad x 8] B tile: bias_hi | bias_lo | 0...
     }
+    lay.ones = take(kRows * 32, 128);
     lay.misc = take(8 + 8 * kGroups, 16);
     lay.total = off;
     lay.group_cols = nmax <= 32 ? 32 : (nmax <= 64 ? 64 : 128);
