@@ -38,7 +38,7 @@
 namespace tgn {
 namespace {
 
-constexpr int kT = 256;            // sort kernel
+constexpr int kT = 512;            // sort kernel (latency-bound: more warps per cloud = shorter serial loops)
 constexpr int kNW = kT / 32;
 constexpr int kMT = 512;           // main kernel
 constexpr int kMNW = kMT / 32;
