@@ -105,8 +105,11 @@ def test_point_transformer_layer_core():
     # above views channels as (s, c/s), i.e. weight index = channel % (c/s) as well
     out_b.square().sum().backward()
     assert rel_err(out_a, out_b) < 1e-5
+    # x_k[n] is constant along the softmax axis, so its true gradient is 0 (both paths return
+    # rounding noise ~1e-8): compare every gradient on the scale of the largest one
+    scale = max(float(t.grad.abs().max()) for t in (x_q, x_k, x_v, p_r))
     for ga, t in zip(grads_a, (x_q, x_k, x_v, p_r)):
-        assert rel_err(ga, t.grad) < 1e-4
+        assert float((ga - t.grad).abs().max()) < 1e-4 * scale
 
 
 def test_transition_up_interpolation():

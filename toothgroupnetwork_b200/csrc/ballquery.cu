@@ -118,6 +118,61 @@ ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__
     }
 }
 
+// ---- streaming variant (default) ------------------------------------------------------------------
+// pack: (x, y, z) -> (x, y, z, |p|^2) so that the scan needs ONE 16-byte load per point.
+__global__ void __launch_bounds__(256)
+pack_xyzn_kernel(size_t total, const float* __restrict__ xyz, float4* __restrict__ out)
+{
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+        out[i] = make_float4(x, y, z, sq_norm_unfused(x, y, z));
+    }
+}
+
+// One warp per query, warps fully independent (no shared memory, no block barrier): every warp
+// scans its cloud from index 0 in steps of 128 points (4 x 16-byte loads in flight per lane) and
+// leaves as soon as it has its nsample hits.  All queries of a cloud start at the same addresses,
+// so the head of the cloud stays L1-resident.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+ball_query_stream_kernel(int N, int S, float r2, int nsample, const float4* __restrict__ pts, const float* __restrict__ new_xyz,
+                         IdxT* __restrict__ group_idx)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * 8 + warp;
+    if (q >= S) return;
+    const float* a = new_xyz + 3 * (static_cast<size_t>(b) * S + q);
+    const float ax = __ldg(a), ay = __ldg(a + 1), az = __ldg(a + 2);
+    const float an = sq_norm_unfused(ax, ay, az);
+    IdxT* row = group_idx + (static_cast<size_t>(b) * S + q) * nsample;
+    const float4* P = pts + static_cast<size_t>(b) * N;
+    int cnt = 0, first = N;
+    for (int o = 0; o < N && cnt < nsample; o += 128) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = o + 32 * u + lane;
+            v[u] = i < N ? __ldg(P + i) : make_float4(0.f, 0.f, 0.f, INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool hit = !(sq_dist_expanded(ax, ay, az, an, v[u].x, v[u].y, v[u].z, v[u].w) > r2);
+            const unsigned mask = __ballot_sync(FULL, hit);
+            if (mask) {
+                if (cnt == 0) first = o + 32 * u + __ffs(mask) - 1;
+                const int pos = cnt + __popc(mask & ((1u << lane) - 1));
+                if (hit && pos < nsample) row[pos] = static_cast<IdxT>(o + 32 * u + lane);
+                cnt += __popc(mask);
+            }
+        }
+    }
+    cnt = min(cnt, nsample);
+    for (int p = cnt + lane; p < nsample; p += 32) row[p] = static_cast<IdxT>(first);
+}
+
 // 3 nearest coarse points per fine point; one thread per fine point, coarse cloud in shared tiles.
 // Strict '<' keeps the lower index among equal distances.
 template <int THREADS>
@@ -199,6 +254,27 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
     if (N <= 0) { set_error("ball_query: N must be positive"); return TGN_ERR_INVALID; }
     if (B > 65535) { set_error("ball_query: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Streaming variant: pack once (stream-ordered scratch), then independent warps.
+    {
+        keep_async_pool();
+        const size_t total = static_cast<size_t>(B) * N;
+        float4* packed = nullptr;
+        const cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&packed), total * sizeof(float4), st);
+        if (e == cudaSuccess) {
+            const int pg = static_cast<int>(std::min<size_t>((total + 255) / 256, 16 * static_cast<size_t>(sm_count())));
+            pack_xyzn_kernel<<<pg, 256, 0, st>>>(total, xyz, packed);
+            int rc = check_launch("pack_xyzn_kernel");
+            if (rc == TGN_OK) {
+                dim3 grid((S + 7) / 8, B);
+                if (idx64) ball_query_stream_kernel<long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<long long*>(group_idx));
+                else ball_query_stream_kernel<int><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<int*>(group_idx));
+                rc = check_launch("ball_query_stream_kernel");
+            }
+            (void)cudaFreeAsync(packed, st);
+            return rc;
+        }
+        (void)cudaGetLastError();     // no scratch: fall through to the shared-memory tile kernel
+    }
     // 16 queries per CTA when that still gives >= 2 waves, else 8 (small batches)
     const bool wide = static_cast<long long>(B) * ((S + 15) / 16) >= 2LL * sm_count();
     if (wide) {

@@ -14,6 +14,7 @@ namespace tgn {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> status (+ message)
 int sm_count();
+void keep_async_pool();               // configure the default cudaMallocAsync pool to cache freed scratch
 
 // ---------------------------------------------------------------- packed fp32x2 (FADD2/FMUL2/FFMA2)
 // Each lane of a packed op is an IEEE round-to-nearest fp32 operation, so a sequence of packed

@@ -468,16 +468,7 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     const size_t o_pts = take(pts * sizeof(float4)), o_t = take(pts * sizeof(float)), o_ka = take(pts * sizeof(uint2)),
                  o_kb = take(pts * sizeof(uint2)), o_lo = take(nbt * sizeof(float4)), o_hi = take(nbt * sizeof(float4)),
                  o_bv = take(nbt * sizeof(int2)), o_bx = take(nbt * sizeof(float4));
-    if (!g_pool_configured) {            // keep freed blocks in the pool instead of returning them to the OS
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        (void)cudaGetLastError();
-        g_pool_configured = true;
-    }
+    keep_async_pool();
     unsigned char* base = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&base), off, stream);
     if (e != cudaSuccess) { set_error("furthestsampling: workspace of %zu bytes: %s", off, cudaGetErrorString(e)); (void)cudaGetLastError(); return TGN_ERR_CUDA; }

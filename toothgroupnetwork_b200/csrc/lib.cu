@@ -31,6 +31,22 @@ int check_launch(const char* what)
     return TGN_OK;
 }
 
+// Stream-ordered scratch (cudaMallocAsync) is used by the bucket FPS and the ball query; keep freed
+// blocks in the device's default pool instead of returning them to the OS at every synchronisation.
+void keep_async_pool()
+{
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    (void)cudaGetLastError();
+    done = true;
+}
+
 int sm_count()
 {
     static int cached = 0;
