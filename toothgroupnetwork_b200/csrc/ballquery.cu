@@ -13,6 +13,7 @@
 //      d = -2*dot; d += |a|^2; d += |b|^2      with |p|^2 = (x*x + y*y) + z*z, unfused
 // and a point is a member iff !(d > r2), r2 = float32(radius**2).
 #include <algorithm>
+#include <climits>
 
 #include "common.cuh"
 #include "tgn_b200.h"
@@ -55,6 +56,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint64_t lds_f32x2(uint32_t addr) {      // two adjacent floats as a packed pair
+    uint64_t v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
 
 // One warp per query, WARPS queries of one cloud per CTA.  Lanes test 32 consecutive points per
 // step; __ballot + popc give each hit its rank in ascending index order.
@@ -64,7 +70,7 @@ ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__
                   IdxT* __restrict__ group_idx)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ float sx[kTile], sy[kTile], sz[kTile], sn[kTile];
+    __shared__ __align__(16) float sx[kTile], sy[kTile], sz[kTile], sn[kTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int q = blockIdx.x * WARPS + warp;
@@ -89,23 +95,39 @@ ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__
         if (cnt < nsample) {
             // four 32-point steps per trip: 16 shared loads issued together, one early-exit test per 128
             // points (the tile arrays are padded to a multiple of 128 with points that can never hit)
+            // Each lane tests the ADJACENT points 2*lane and 2*lane+1 of a 64-point step with packed
+            // fp32x2 arithmetic (FMUL2/FFMA2/FADD2: same IEEE-rn results per element, half the issue
+            // slots of an issue-bound kernel); two steps per trip.
+            const uint64_t AX = pack2(ax, ax), AY = pack2(ay, ay), AZ = pack2(az, az), AN = pack2(an, an);
+            const uint64_t M2 = pack2(-2.0f, -2.0f);
+            const unsigned lt = (1u << lane) - 1u;
             for (int o = 0; o < tile && cnt < nsample; o += 128) {
-                float d[4];
+                uint64_t d[2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t off = static_cast<uint32_t>(o + 32 * u + lane) * 4u;
-                    d[u] = sq_dist_expanded(ax, ay, az, an, lds_f32(a_x + off), lds_f32(a_y + off), lds_f32(a_z + off),
-                                            lds_f32(a_n + off));
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t off = static_cast<uint32_t>(o + 64 * u + 2 * lane) * 4u;
+                    uint64_t dot = mul2(AX, lds_f32x2(a_x + off));
+                    dot = fma2(AY, lds_f32x2(a_y + off), dot);
+                    dot = fma2(AZ, lds_f32x2(a_z + off), dot);
+                    d[u] = add2(add2(mul2(M2, dot), AN), lds_f32x2(a_n + off));
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool hit = !(d[u] > r2);
-                    const unsigned mask = __ballot_sync(FULL, hit);
-                    if (mask) {
-                        if (cnt == 0) first = base + o + 32 * u + __ffs(mask) - 1;
-                        const int pos = cnt + __popc(mask & ((1u << lane) - 1));
-                        if (hit && pos < nsample) row[pos] = static_cast<IdxT>(base + o + 32 * u + lane);
-                        cnt += __popc(mask);
+                for (int u = 0; u < 2; ++u) {
+                    float d0, d1;
+                    unpack2(d[u], d0, d1);
+                    const bool h0 = !(d0 > r2), h1 = !(d1 > r2);
+                    const unsigned m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
+                    if (m0 | m1) {
+                        const int p0 = base + o + 64 * u;               // index of point (lane 0, half 0)
+                        if (cnt == 0) {
+                            const int f0 = m0 ? 2 * (__ffs(m0) - 1) : INT_MAX, f1 = m1 ? 2 * (__ffs(m1) - 1) + 1 : INT_MAX;
+                            first = p0 + min(f0, f1);
+                        }
+                        const int before = cnt + __popc(m0 & lt) + __popc(m1 & lt);   // hits at lower indices
+                        if (h0 && before < nsample) row[before] = static_cast<IdxT>(p0 + 2 * lane);
+                        const int pos1 = before + (h0 ? 1 : 0);
+                        if (h1 && pos1 < nsample) row[pos1] = static_cast<IdxT>(p0 + 2 * lane + 1);
+                        cnt += __popc(m0) + __popc(m1);
                     }
                 }
             }
@@ -254,8 +276,10 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
     if (N <= 0) { set_error("ball_query: N must be positive"); return TGN_ERR_INVALID; }
     if (B > 65535) { set_error("ball_query: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // Streaming variant: pack once (stream-ordered scratch), then independent warps.
-    {
+    // Streaming variant (pack once into stream-ordered scratch, then fully independent warps).  Measured
+    // on B200 it ties with the shared-memory tile kernel at 24k points (both issue-bound) and loses
+    // to its packed-fp32x2 form, so it is only taken on request (idx64 bit 1 set: experiments).
+    if (idx64 & 2) {
         keep_async_pool();
         const size_t total = static_cast<size_t>(B) * N;
         float4* packed = nullptr;
@@ -266,7 +290,7 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
             int rc = check_launch("pack_xyzn_kernel");
             if (rc == TGN_OK) {
                 dim3 grid((S + 7) / 8, B);
-                if (idx64) ball_query_stream_kernel<long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<long long*>(group_idx));
+                if (idx64 & 1) ball_query_stream_kernel<long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<long long*>(group_idx));
                 else ball_query_stream_kernel<int><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<int*>(group_idx));
                 rc = check_launch("ball_query_stream_kernel");
             }
@@ -279,11 +303,11 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
     const bool wide = static_cast<long long>(B) * ((S + 15) / 16) >= 2LL * sm_count();
     if (wide) {
         dim3 grid((S + 15) / 16, B);
-        if (idx64) ball_query_kernel<16, long long><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
+        if (idx64 & 1) ball_query_kernel<16, long long><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
         else ball_query_kernel<16, int><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx));
     } else {
         dim3 grid((S + 7) / 8, B);
-        if (idx64) ball_query_kernel<8, long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
+        if (idx64 & 1) ball_query_kernel<8, long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
         else ball_query_kernel<8, int><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx));
     }
     return check_launch("ball_query_kernel");
