@@ -40,6 +40,9 @@ MLP = [32, 32, 64]
 METRIC = "sampled-points/sec (FPS+ballq+group-MLP, 24k-pt cloud)"
 UNIT = "sampled points/s"
 WORKLOAD = "pointnet++ SA1 forward: FPS 24000->1024, ball query r=0.1 K=32, group-MLP 9->[32,32,64], eval BN"
+# dram__bytes_read.sum + dram__bytes_write.sum of fps_bucket_sort_kernel + fps_bucket_kernel<256> in one
+# `ncu --set full` capture of this bench at 592 clouds (profiles/r1c_ncu_full_raw.csv): 7.42 GB per launch pair
+NCU_FPS_DRAM_BYTES_PER_CLOUD = (4.689534e9 + 0.497730e9 + 1.350417e9 + 0.885668e9) / 592
 
 
 def host_cores() -> int:
@@ -329,9 +332,13 @@ def main():
         "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "stage_ms": {"fps": fps_ms, "ball_query": ball_ms, "group_mlp": mlp_ms},
-        "roofline": {"kernel": "fps_resident_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
-                     "note": "algorithmic bytes are served from registers by design; compulsory HBM bytes are 12N+4M per cloud"},
+        "roofline": {"kernel": "fps_bucket_kernel (+ its sort prologue; one event pair brackets both)", "bound": "hbm",
+                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": NCU_FPS_DRAM_BYTES_PER_CLOUD * B, "peak_kind": peak_kind,
+                     "dram_achieved_gbs": NCU_FPS_DRAM_BYTES_PER_CLOUD * B / (fps_ms * 1e-3) / 1e9,
+                     "note": "achieved = algorithmic 20*(M-1)*N*B bytes / FPS time; frac > 1 because the exact "
+                             "bucket pruning never touches ~97% of those point-updates (profiles/r1_summary.md). "
+                             "traffic = ncu dram read+write of the same launches (profiles/r1c_ncu_full_raw.csv), scaled per cloud"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_feats.numel() * 4),
                 "d2h_bytes_per_step": int((out_xyz_host.numel() + out_pts_host.numel()) * 4)},
         "gpu_launches": int(agg["launches"]),
