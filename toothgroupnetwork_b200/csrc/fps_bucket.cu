@@ -43,7 +43,9 @@ constexpr int kNW = kT / 32;
 constexpr int kMT = 512;           // main kernel
 constexpr int kMNW = kMT / 32;
 constexpr int kBatch = 4;          // buckets a warp keeps in flight (memory-level parallelism)
+constexpr int kGatherUnroll = 4;   // buckets a sort-kernel warp gathers together
 constexpr int kRadixUnroll = 4;    // radix steps whose loads are issued together
+constexpr int kSmemSortMaxN = 26624; // clouds up to this size are radix-sorted in shared memory (2 x 4 B per point)
 constexpr int kMaxBuckets = 3600;   // 60 B of shared memory per bucket
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -86,6 +88,14 @@ __device__ __forceinline__ unsigned spread3(unsigned x) {   // 10 bits -> every 
     x = (x | (x << 2)) & 0x09249249u;
     return x;
 }
+// Warp min / max of floats through the integer CREDUX path (order-preserving bit map; +-inf allowed).
+__device__ __forceinline__ int float_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7FFFFFFF)); }
+__device__ __forceinline__ float ordered_min(float v) { return ordered_float(__reduce_min_sync(FULL, float_ordered(v))); }
+__device__ __forceinline__ float ordered_max(float v) { return ordered_float(__reduce_max_sync(FULL, float_ordered(v))); }
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
@@ -97,11 +107,32 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// One stable LSD radix pass on 7 bits.  Warp w owns a contiguous range of the input; ranks inside
-// a 32-element step come from __match_any_sync, so the pass is deterministic.
-__device__ void radix_pass7(const uint2* __restrict__ src, uint2* __restrict__ dst, int n, int shift,
-                            int (*hist)[128], int* dig_base)
+// Sort elements: (Morton code, index) pairs in global memory, or one packed word (code << 15 | index)
+// when a cloud is small enough to be sorted entirely in shared memory.
+__device__ __forceinline__ unsigned radix_key(uint2 e) { return e.x; }
+__device__ __forceinline__ unsigned radix_key(unsigned e) { return e; }
+
+// Lanes of the warp holding the same BITS-bit digit as the caller (what __match_any_sync returns, but
+// built from BITS + 1 ballots: MATCH.ANY costs a few hundred cycles when most lanes differ).
+template <int BITS>
+__device__ __forceinline__ unsigned peer_mask(unsigned d, bool ok) {
+    unsigned m = __ballot_sync(FULL, ok);
+#pragma unroll
+    for (int b = 0; b < BITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(FULL, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
+// One stable LSD radix pass on BITS <= 7 bits of (key >> shift).  Warp w owns a contiguous range of the
+// input; ranks inside a 32-element step come from the peer masks, so the pass is deterministic.
+template <typename E, int BITS>
+__device__ __forceinline__ void radix_pass(const E* __restrict__ src, E* __restrict__ dst, int n, int shift,
+                                           int (*hist)[128], int* dig_base)
 {
+    constexpr unsigned mask = (1u << BITS) - 1u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per_warp = ((n + kNW - 1) / kNW + 31) & ~31;
     const int lo = warp * per_warp, hi = min(n, lo + per_warp);
@@ -112,14 +143,14 @@ __device__ void radix_pass7(const uint2* __restrict__ src, uint2* __restrict__ d
 #pragma unroll
         for (int u = 0; u < kRadixUnroll; ++u) {          // independent loads first (L2 latency paid once)
             const int i = base + 32 * u + lane;
-            code[u] = i < hi ? src[i].x : 0u;
+            code[u] = i < hi ? radix_key(src[i]) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < kRadixUnroll; ++u) {
             const int i = base + 32 * u + lane;
             const bool ok = i < hi;
-            const int d = ok ? static_cast<int>((code[u] >> shift) & 127u) : 128 + lane;   // unique dummy digits
-            const unsigned m = __match_any_sync(FULL, d);
+            const int d = static_cast<int>((code[u] >> shift) & mask);
+            const unsigned m = peer_mask<BITS>(d, ok);
             if (ok && lane == __ffs(m) - 1) hist[warp][d] += __popc(m);
             __syncwarp();
         }
@@ -153,18 +184,18 @@ __device__ void radix_pass7(const uint2* __restrict__ src, uint2* __restrict__ d
     }
     __syncthreads();
     for (int base = lo; base < hi; base += 32 * kRadixUnroll) {
-        uint2 el[kRadixUnroll];
+        E el[kRadixUnroll];
 #pragma unroll
         for (int u = 0; u < kRadixUnroll; ++u) {
             const int i = base + 32 * u + lane;
-            el[u] = i < hi ? src[i] : make_uint2(0u, 0u);
+            el[u] = i < hi ? src[i] : E{};
         }
 #pragma unroll
         for (int u = 0; u < kRadixUnroll; ++u) {
             const int i = base + 32 * u + lane;
             const bool ok = i < hi;
-            const int d = ok ? static_cast<int>((el[u].x >> shift) & 127u) : 128 + lane;
-            const unsigned m = __match_any_sync(FULL, d);
+            const int d = static_cast<int>((radix_key(el[u]) >> shift) & mask);
+            const unsigned m = peer_mask<BITS>(d, ok);
             const int rank = __popc(m & ((1u << lane) - 1u));
             int cur = 0;
             if (ok) cur = hist[warp][d];
@@ -179,10 +210,14 @@ __device__ void radix_pass7(const uint2* __restrict__ src, uint2* __restrict__ d
     __syncthreads();
 }
 
+// SMEM_ = true: clouds of at most kSmemSortMaxN points; the three radix passes ping-pong between two
+// shared-memory arrays of packed words (17-bit Morton code, 15-bit point index) instead of global memory.
+template <bool SMEM_>
 __global__ void __launch_bounds__(kT)
 fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const float* __restrict__ tmp,
-                       BucketWs ws, int bs_log2)
+                       BucketWs ws, int bs_log2, int spad)
 {
+    extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ float red[6][kNW];
     __shared__ float box[6];
     __shared__ int hist[kNW][128];
@@ -224,65 +259,86 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float ext = box[3 + a] - box[a];
-        inv[a] = ext > 0.f ? 127.999f / ext : 0.f;
+        inv[a] = ext > 0.f ? (static_cast<float>(1 << (SMEM_ ? (a == 2 ? 5 : 6) : 7)) - 0.001f) / ext : 0.f;
         scale = fmaxf(scale, fmaxf(fabsf(box[a]), fabsf(box[3 + a])));
     }
     const float slack = 4e-6f * scale;       // absolute inflation of every bucket box
 
     // ---- Morton keys + stable radix sort ----------------------------------------------------------------
+    unsigned* sa = reinterpret_cast<unsigned*>(dyn);
+    unsigned* sb = sa + spad;
     for (int j = tid; j < n; j += kT) {
         unsigned code = 0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
+            const unsigned qmax = (1u << (SMEM_ ? (a == 2 ? 5 : 6) : 7)) - 1u;
             const float v = __ldg(cx + 3 * static_cast<size_t>(j) + a);
-            const unsigned q = min(127u, static_cast<unsigned>(fmaxf((v - box[a]) * inv[a], 0.f)));
+            const unsigned q = min(qmax, static_cast<unsigned>(fmaxf((v - box[a]) * inv[a], 0.f)));
             code |= spread3(q) << a;
         }
-        ka[j] = make_uint2(code, static_cast<unsigned>(j));
+        if (SMEM_) sa[j] = (code << 15) | static_cast<unsigned>(j);
+        else ka[j] = make_uint2(code, static_cast<unsigned>(j));
     }
     __syncthreads();
-    radix_pass7(ka, kb, n, 0, hist, dig_base);
-    radix_pass7(kb, ka, n, 7, hist, dig_base);
-    radix_pass7(ka, kb, n, 14, hist, dig_base);
-    const uint2* sorted = kb;
+    if (SMEM_) {
+        radix_pass<unsigned, 6>(sa, sb, n, 15, hist, dig_base);
+        radix_pass<unsigned, 6>(sb, sa, n, 21, hist, dig_base);
+        radix_pass<unsigned, 5>(sa, sb, n, 27, hist, dig_base);
+    } else {
+        radix_pass<uint2, 7>(ka, kb, n, 0, hist, dig_base);
+        radix_pass<uint2, 7>(kb, ka, n, 7, hist, dig_base);
+        radix_pass<uint2, 7>(ka, kb, n, 14, hist, dig_base);
+    }
 
-    // ---- sorted points and their running minima -----------------------------------------------------------
+    // ---- sorted points, running minima, bucket boxes and initial candidates -------------------------------
+    // A warp writes one bucket (32 consecutive sorted points) per step and reduces its box and best
+    // candidate from the registers it just filled; kGatherUnroll buckets are in flight per warp.
     const int npad = (n + 31) & ~31;
-    for (int p = tid; p < npad; p += kT) {
-        if (p < n) {
-            const int j = static_cast<int>(sorted[p].y);
-            pts4[p] = make_float4(__ldg(cx + 3 * static_cast<size_t>(j)), __ldg(cx + 3 * static_cast<size_t>(j) + 1),
-                                  __ldg(cx + 3 * static_cast<size_t>(j) + 2), __int_as_float(point_key(j, bs_log2)));
-            tval[p] = tmp ? tmp[start_n + j] : 1e10f;
-        } else {
-            pts4[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(INT_MAX));
-            tval[p] = -1.0f;
-        }
-    }
-    __syncthreads();
-
-    // ---- bucket boxes and initial candidates --------------------------------------------------------------
     const int nb = npad >> 5;
-    float4* blo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
-    float4* bhi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
-    int2* bvk = ws.bvk + static_cast<size_t>(cloud) * ws.nbmax;
-    float4* bxyz = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
-    for (int bk = warp; bk < nb; bk += kNW) {
-        const float4 P = pts4[bk * 32 + lane];
-        const float tv = tval[bk * 32 + lane];
-        const int key = __float_as_int(P.w);
-        const bool ok = key != INT_MAX;
-        const float lx = warp_min(ok ? P.x : INFINITY), hx = warp_max(ok ? P.x : -INFINITY);
-        const float ly = warp_min(ok ? P.y : INFINITY), hy = warp_max(ok ? P.y : -INFINITY);
-        const float lz = warp_min(ok ? P.z : INFINITY), hz = warp_max(ok ? P.z : -INFINITY);
-        const int bi = __float_as_int(tv);
-        const int wmax = __reduce_max_sync(FULL, bi);
-        const int wkey = __reduce_min_sync(FULL, bi == wmax ? key : INT_MAX);
-        if (lane == 0) {
-            blo[bk] = make_float4(lx - slack, ly - slack, lz - slack, __int_as_float(wmax));
-            bhi[bk] = make_float4(hx + slack, hy + slack, hz + slack, 0.f);
+    float4* __restrict__ blo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
+    float4* __restrict__ bhi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
+    int2* __restrict__ bvk = ws.bvk + static_cast<size_t>(cloud) * ws.nbmax;
+    float4* __restrict__ bxyz = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
+    for (int bk0 = warp; bk0 < nb; bk0 += kNW * kGatherUnroll) {
+        int j[kGatherUnroll];
+        float4 P[kGatherUnroll];
+        float tv[kGatherUnroll];
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            const int p = (bk0 + u * kNW) * 32 + lane;
+            j[u] = p < n ? (SMEM_ ? static_cast<int>(sb[p] & 0x7FFFu) : static_cast<int>(kb[p].y)) : -1;
         }
-        if (bi == wmax && key == wkey) { bvk[bk] = make_int2(wmax, wkey); bxyz[bk] = P; }
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            if (j[u] >= 0) {
+                const float* q = cx + 3 * static_cast<size_t>(j[u]);
+                P[u] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __int_as_float(point_key(j[u], bs_log2)));
+                tv[u] = tmp ? __ldg(tmp + start_n + j[u]) : 1e10f;
+            } else {
+                P[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(INT_MAX));
+                tv[u] = -1.0f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            const int bk = bk0 + u * kNW;
+            if (bk >= nb) break;                      // warp-uniform
+            pts4[bk * 32 + lane] = P[u];
+            tval[bk * 32 + lane] = tv[u];
+            const bool ok = j[u] >= 0;
+            const float lx = ordered_min(ok ? P[u].x : INFINITY), hx = ordered_max(ok ? P[u].x : -INFINITY);
+            const float ly = ordered_min(ok ? P[u].y : INFINITY), hy = ordered_max(ok ? P[u].y : -INFINITY);
+            const float lz = ordered_min(ok ? P[u].z : INFINITY), hz = ordered_max(ok ? P[u].z : -INFINITY);
+            const int key = __float_as_int(P[u].w);
+            const int bi = __float_as_int(tv[u]);
+            const int wmax = __reduce_max_sync(FULL, bi);
+            const int wkey = __reduce_min_sync(FULL, bi == wmax ? key : INT_MAX);
+            if (lane == 0) {
+                blo[bk] = make_float4(lx - slack, ly - slack, lz - slack, __int_as_float(wmax));
+                bhi[bk] = make_float4(hx + slack, hy + slack, hz + slack, 0.f);
+            }
+            if (bi == wmax && key == wkey) { bvk[bk] = make_int2(wmax, wkey); bxyz[bk] = P[u]; }
+        }
     }
 }
 
@@ -481,7 +537,19 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     ws.bvk = reinterpret_cast<int2*>(base + o_bv);
     ws.bxyz = reinterpret_cast<float4*>(base + o_bx);
 
-    fps_bucket_sort_kernel<<<b, kT, 0, stream>>>(xyz, offset, tmp, ws, bs_log2);
+    if (n_max <= kSmemSortMaxN) {
+        const int spad = (n_max + 31) & ~31;
+        const size_t sort_smem = 2 * sizeof(unsigned) * static_cast<size_t>(spad);
+        static bool sort_attr = false;
+        if (!sort_attr) {
+            cudaFuncSetAttribute(fps_bucket_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(2 * sizeof(unsigned) * kSmemSortMaxN));
+            sort_attr = true;
+        }
+        fps_bucket_sort_kernel<true><<<b, kT, sort_smem, stream>>>(xyz, offset, tmp, ws, bs_log2, spad);
+    } else {
+        fps_bucket_sort_kernel<false><<<b, kT, 0, stream>>>(xyz, offset, tmp, ws, bs_log2, 0);
+    }
     int rc = check_launch("fps_bucket_sort_kernel");
     if (rc == TGN_OK) {
         const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 3 + sizeof(int2) + sizeof(int));
