@@ -103,6 +103,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
+// Same, but the probe itself may suspend the warp in hardware for up to ~10 ms (no polling instructions
+// competing with the warps that have work): for waits on tensor-core completion.
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
 // Asynchronous remote store that also completes `bytes` on the destination CTA's mbarrier
 // (both addresses are shared::cluster addresses obtained with map_to_cta).
 __device__ __forceinline__ void st_async_v4(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar) {

@@ -19,8 +19,12 @@
 //     ("3xTF32"), so the result carries ~2^-21 relative error instead of tf32's 2^-10 -- the
 //     reference's own default for these 1x1 convolutions is plain TF32;
 //   * one elected thread per group issues the MMAs and tcgen05.commit's the group's mbarrier;
-//   * the max over the K rows of a neighbourhood is a CREDUX per output channel when K is 16 or 32
-//     (the rows of a neighbourhood are the lanes of one warp), a shared-memory pass otherwise.
+//   * the LAST layer runs transposed, D^T[channel, row] = W[channel, K] * X[row, K]^T: the weights
+//     (zero-padded to 128 channels) are the A operand and the activation tile -- already in the
+//     canonical K-major layout -- is the B operand (N = 128 rows).  A TMEM lane is then an output
+//     channel and its 128 columns are the rows of the tile, so the max over the K rows of a
+//     neighbourhood is a chain of 3-input FMNMX inside ONE thread (no cross-lane reduction, no
+//     partial buffers) and the thread stores the channel-first output directly.
 // Weights are split and laid out once per CTA; CTAs are persistent over tiles.
 #include <algorithm>
 
@@ -41,13 +45,13 @@ struct TcLayout {
     int kpad[kSaMaxLayers];          // K of layer l, multiple of 8
     int npad[kSaMaxLayers];          // N of layer l, multiple of 16
     uint32_t w_hi[kSaMaxLayers], w_lo[kSaMaxLayers], bias[kSaMaxLayers];   // byte offsets in dynamic smem
-    uint32_t a_hi[kGroups], a_lo[kGroups];   // per group A operands; a_hi doubles as fp32 staging for generic K
-    uint32_t part[kGroups];          // per group: up to 8 per-warp partial maxima rows of npad floats
-    uint32_t ones;                   // constant [128 x 8] A tile that adds the bias through the MMA
+    uint32_t a_hi[kGroups], a_lo[kGroups];   // per group activation operands (A of the inner layers, B of the last)
+    uint32_t ones;                   // constant [128 x 8] tile that adds the bias through the MMA
     uint32_t misc;                   // tmem base (u32) @0, group mbarriers (u64) @8+8g
     uint32_t total;
     uint32_t tmem_cols, group_cols;
-    int tiles_per_cloud, gpt, stage_stride;
+    int tiles_per_cloud, gpt;
+    uint32_t tpc_magic;              // floor(2^32 / tiles_per_cloud): t / tiles_per_cloud by IMAD.HI + one fix-up
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -110,6 +114,40 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Inner-layer epilogue of one thread: its accumulator lane (NP columns) -> bias is already in, ReLU,
+// tf32 hi/lo split, 16-byte stores into the next layer's K-major operand (row r).
+template <int NP>
+__device__ __forceinline__ void mid_epilogue(uint32_t tmem_row, uint32_t a_hi, uint32_t a_lo, int r)
+{
+#pragma unroll
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+        uint32_t v[32];
+        const bool full = NP - c0 >= 32;             // NP is a multiple of 16: a chunk is 32 or 16 wide
+        if (full) tmem_ld32(tmem_row + c0, v);
+        else tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            if (i < 16 || full) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) split_tf32(fmaxf(__uint_as_float(v[i + u]), 0.f), hi[u], lo[u]);
+                const uint32_t off = static_cast<uint32_t>((c0 + i) >> 2) * kChunkStrideA + r * 16;
+                st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+}
+
+// max(0, v[B], ..., v[B+15]) with 3-input FMNMX
+template <int B>
+__device__ __forceinline__ float relu_max16(const uint32_t (&v)[32]) {
+    float m = max3(0.f, __uint_as_float(v[B]), __uint_as_float(v[B + 1]));
+#pragma unroll
+    for (int i = 2; i < 16; i += 2) m = max3(m, __uint_as_float(v[B + i]), __uint_as_float(v[B + i + 1]));
+    return m;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 {
@@ -117,7 +155,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = tid / kRows;                 // tile group
-    const int r = tid - g * kRows;             // row inside the tile
+    const int r = tid - g * kRows;             // row inside the tile (inner layers) / output channel (last layer)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + lay.misc);
     const uint32_t bar = sbase + lay.misc + 8 + 8 * g;
 
@@ -126,9 +164,12 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (r == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    // ---- weights: split into tf32 hi/lo, canonical K-major layout (LBO = npad*16, SBO = 128) -------
+    // ---- weights: split into tf32 hi/lo, canonical K-major layout.  Inner layers: B operand
+    //      [npad x kpad] (LBO = npad*16); last layer: A operand [128 x kpad] (LBO = 128*16), zero rows
+    //      beyond cout.  SBO = 128 either way.
     for (int l = 0; l < p.L; ++l) {
-        const int cin = p.ch[l], cout = p.ch[l + 1], kp = lay.kpad[l], np = lay.npad[l];
+        const int cin = p.ch[l], cout = p.ch[l + 1], kp = lay.kpad[l];
+        const int np = l == p.L - 1 ? kRows : lay.npad[l];
         for (int e = tid; e < np * kp; e += kThreads) {
             const int n = e / kp, k = e - n * kp;
             const float w = (n < cout && k < cin) ? __ldg(p.W[l] + static_cast<size_t>(n) * cin + k) : 0.f;
@@ -138,8 +179,8 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             *reinterpret_cast<uint32_t*>(smem + lay.w_hi[l] + off) = hi;
             *reinterpret_cast<uint32_t*>(smem + lay.w_lo[l] + off) = lo;
         }
-        // bias as a B operand of one extra K=8 step: column k=0 holds bias_hi, k=1 bias_lo (rest 0);
-        // multiplied by the constant "ones" A tile below it adds bias_hi + bias_lo to every row.
+        // bias as one extra K=8 step: column k=0 holds bias_hi, k=1 bias_lo (rest 0); multiplied by
+        // the constant "ones" tile it adds bias_hi + bias_lo to every row.
         for (int e = tid; e < np * 8; e += kThreads) {
             const int n = e >> 3, k = e & 7;
             uint32_t hi = 0u, lo = 0u;
@@ -148,7 +189,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             *reinterpret_cast<uint32_t*>(smem + lay.bias[l] + off) = k == 0 ? hi : (k == 1 ? lo : 0u);
         }
     }
-    // constant A tile [128 rows x 8]: columns 0 and 1 are 1.0 (exact in tf32), the rest 0
+    // constant tile [128 x 8]: columns 0 and 1 are 1.0 (exact in tf32), the rest 0
     for (int e = tid; e < kRows * 8; e += kThreads) {
         const int rr = e >> 3, k = e & 7;
         *reinterpret_cast<float*>(smem + lay.ones + static_cast<uint32_t>(k >> 2) * kChunkStrideA + rr * 16 + (k & 3) * 4) =
@@ -163,44 +204,54 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
     const uint32_t a_hi = sbase + lay.a_hi[g], a_lo = sbase + lay.a_lo[g];
     uint32_t phase = 0;
 
-    const int cin0 = p.ch[0];
     const int cout_last = p.ch[p.L];
     const int total_tiles = lay.tiles_per_cloud * p.B;
     const int tile_step = gridDim.x * kGroups;
-    const bool lane_max = (p.K == 16 || p.K == 32 || p.K == 64 || p.K == 128);
-    float* part = reinterpret_cast<float*>(smem + lay.part[g]);
     const uint64_t desc_a_hi = make_smem_desc(a_hi, kChunkStrideA, 128);
     const uint64_t desc_a_lo = make_smem_desc(a_lo, kChunkStrideA, 128);
     const int xoff = p.xyz_first ? 0 : p.D;       // first channel of the xyz_rel block
     const int foff = p.xyz_first ? 3 : 0;         // first channel of the feature block
+    const int r_div_k = r / p.K;                  // neighbourhood of this thread's row inside a tile
+    // t / tiles_per_cloud without an integer division (magic = floor(2^32 / d) is off by at most one)
+    auto cloud_of = [&](int t) -> int {
+        int q = static_cast<int>(__umulhi(static_cast<unsigned>(t), lay.tpc_magic));
+        if (t - q * lay.tiles_per_cloud >= lay.tiles_per_cloud) ++q;
+        return q;
+    };
     // neighbour index of this thread's row in tile `t` (-1 past the end / past the rows of the tile)
     auto load_index = [&](int t) -> int {
         if (t >= total_tiles) return -1;
-        const int tb = t / lay.tiles_per_cloud;
+        const int tb = cloud_of(t);
         const int ts0 = (t - tb * lay.tiles_per_cloud) * lay.gpt;
         if (r >= min(lay.gpt, p.S - ts0) * p.K) return -1;
         return __ldg(p.gidx + (static_cast<size_t>(tb) * p.S + ts0) * p.K + r);
     };
     // the 16-wide zero-padded [xyz_rel | feats] (or [feats | xyz_rel]) row of this thread in tile `t`
     auto load_row16 = [&](int t, int j, float (&out)[16]) {
-        const bool ok = t < total_tiles && j >= 0 && j < p.N;
-        const int tb = ok ? t / lay.tiles_per_cloud : 0;
-        const int ts = ok ? (t - tb * lay.tiles_per_cloud) * lay.gpt + r / p.K : 0;
-        const int jj = ok ? j : 0;
-        const float* px = p.xyz + 3 * (static_cast<size_t>(tb) * p.N + jj);
-        const float* pc = p.new_xyz + 3 * (static_cast<size_t>(tb) * p.S + ts);
-        const float* pf = p.feats ? p.feats + (static_cast<size_t>(tb) * p.N + jj) * p.D : px;
-        const float rel0 = __fsub_rn(__ldg(px), __ldg(pc)), rel1 = __fsub_rn(__ldg(px + 1), __ldg(pc + 1)),
-                    rel2 = __fsub_rn(__ldg(px + 2), __ldg(pc + 2));
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const int xc = c - xoff;
-            float v = xc == 0 ? rel0 : (xc == 1 ? rel1 : rel2);
-            if (static_cast<unsigned>(xc) > 2u) {
-                const unsigned fc = static_cast<unsigned>(c - foff);
-                v = fc < static_cast<unsigned>(p.D) ? __ldg(pf + fc) : 0.f;
+        for (int c = 0; c < 16; ++c) out[c] = 0.f;
+        if (t < total_tiles && j >= 0 && j < p.N) {
+            const int tb = cloud_of(t);
+            const int ts = (t - tb * lay.tiles_per_cloud) * lay.gpt + r_div_k;
+            const float* px = p.xyz + 3 * (static_cast<size_t>(tb) * p.N + j);
+            const float* pc = p.new_xyz + 3 * (static_cast<size_t>(tb) * p.S + ts);
+            const float* pf = p.feats ? p.feats + (static_cast<size_t>(tb) * p.N + j) * p.D : px;
+            const float rel0 = __fsub_rn(__ldg(px), __ldg(pc)), rel1 = __fsub_rn(__ldg(px + 1), __ldg(pc + 1)),
+                        rel2 = __fsub_rn(__ldg(px + 2), __ldg(pc + 2));
+            if (p.xyz_first) {
+                out[0] = rel0; out[1] = rel1; out[2] = rel2;
+#pragma unroll
+                for (int i = 0; i < 13; ++i)
+                    if (i < p.D) out[3 + i] = __ldg(pf + i);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c < p.D) out[c] = __ldg(pf + c);
+                    else if (c == p.D) out[c] = rel0;
+                    else if (c == p.D + 1) out[c] = rel1;
+                    else if (c == p.D + 2) out[c] = rel2;
+                }
             }
-            out[c] = ok ? v : 0.f;
         }
     };
     const bool fast_rows = lay.kpad[0] == 16;     // the whole padded input row fits 16 registers
@@ -219,7 +270,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
     }
 
     for (int tile = blockIdx.x * kGroups + g; tile < total_tiles; tile += tile_step) {
-        const int b = tile / lay.tiles_per_cloud;
+        const int b = cloud_of(tile);
         const int s0 = (tile - b * lay.tiles_per_cloud) * lay.gpt;
         const int groups = min(lay.gpt, p.S - s0);
         const int rows = groups * p.K;
@@ -240,7 +291,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             j_next = load_index(tile + 2 * tile_step);
         } else {
             int j = j_next;                               // index prefetched while the previous tile computed
-            const int s = s0 + (r < rows ? r / p.K : 0);
+            const int s = s0 + (r < rows ? r_div_k : 0);
             if (r >= rows || j < 0 || j >= p.N) j = -1;
             const int jj = j < 0 ? 0 : j;
             const float* px = p.xyz + 3 * (static_cast<size_t>(b) * p.N + jj);
@@ -271,6 +322,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 
         for (int l = 0; l < p.L; ++l) {
             const int kp = lay.kpad[l], np = lay.npad[l];
+            const bool last = (l == p.L - 1);
             proxy_fence_async();           // this thread's operand stores -> visible to the tensor core
             tc_fence_before();
             group_sync(g);
@@ -279,115 +331,114 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                 // stays on the uniform datapath); one lane issues.  The start-address field is the low
                 // 14 bits (units of 16 B): a K-step advances it by a constant.
                 tc_fence_after();
-                const uint32_t idesc = make_idesc_tf32(np);
-                const uint32_t lbo_b = static_cast<uint32_t>(np) * 16;
-                uint64_t d_ahi = desc_a_hi, d_alo = desc_a_lo;
-                uint64_t d_bhi = make_smem_desc(sbase + lay.w_hi[l], lbo_b, 128);
-                uint64_t d_blo = make_smem_desc(sbase + lay.w_lo[l], lbo_b, 128);
-                const uint64_t step_a = (2 * kChunkStrideA) >> 4, step_b = (2 * lbo_b) >> 4;
                 const int nks = kp / 8;
-                for (int ks = 0; ks < nks; ++ks) {
-                    if (lane == 0) {
-                        mma_tf32_ss(tmem_base, d_ahi, d_bhi, idesc, ks > 0);
-                        mma_tf32_ss(tmem_base, d_alo, d_bhi, idesc, true);
-                        mma_tf32_ss(tmem_base, d_ahi, d_blo, idesc, true);
+                const uint64_t step_x = (2 * kChunkStrideA) >> 4;
+                uint64_t d_xhi = desc_a_hi, d_xlo = desc_a_lo;
+                if (!last) {
+                    // D[row, n] += X[row, k] * W[n, k]
+                    const uint32_t idesc = make_idesc_tf32(np);
+                    const uint32_t lbo_b = static_cast<uint32_t>(np) * 16;
+                    uint64_t d_whi = make_smem_desc(sbase + lay.w_hi[l], lbo_b, 128);
+                    uint64_t d_wlo = make_smem_desc(sbase + lay.w_lo[l], lbo_b, 128);
+                    const uint64_t step_w = (2 * lbo_b) >> 4;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        if (lane == 0) {
+                            mma_tf32_ss(tmem_base, d_xhi, d_whi, idesc, ks > 0);
+                            mma_tf32_ss(tmem_base, d_xlo, d_whi, idesc, true);
+                            mma_tf32_ss(tmem_base, d_xhi, d_wlo, idesc, true);
+                        }
+                        d_xhi += step_x; d_xlo += step_x; d_whi += step_w; d_wlo += step_w;
                     }
-                    d_ahi += step_a; d_alo += step_a; d_bhi += step_b; d_blo += step_b;
-                }
-                if (lane == 0) {
-                    mma_tf32_ss(tmem_base, make_smem_desc(sbase + lay.ones, kChunkStrideA, 128),
-                                make_smem_desc(sbase + lay.bias[l], lbo_b, 128), idesc, true);     // + bias
-                    mma_commit(bar);       // arrives on the group's mbarrier when the MMAs above have completed
+                    if (lane == 0) {
+                        mma_tf32_ss(tmem_base, make_smem_desc(sbase + lay.ones, kChunkStrideA, 128),
+                                    make_smem_desc(sbase + lay.bias[l], lbo_b, 128), idesc, true);     // + bias
+                        mma_commit(bar);   // arrives on the group's mbarrier when the MMAs above have completed
+                    }
+                } else {
+                    // D^T[channel, row] += W[channel, k] * X[row, k]
+                    const uint32_t idesc = make_idesc_tf32(kRows);
+                    uint64_t d_whi = make_smem_desc(sbase + lay.w_hi[l], kChunkStrideA, 128);
+                    uint64_t d_wlo = make_smem_desc(sbase + lay.w_lo[l], kChunkStrideA, 128);
+                    for (int ks = 0; ks < nks; ++ks) {
+                        if (lane == 0) {
+                            mma_tf32_ss(tmem_base, d_whi, d_xhi, idesc, ks > 0);
+                            mma_tf32_ss(tmem_base, d_whi, d_xlo, idesc, true);
+                            mma_tf32_ss(tmem_base, d_wlo, d_xhi, idesc, true);
+                        }
+                        d_xhi += step_x; d_xlo += step_x; d_whi += step_x; d_wlo += step_x;
+                    }
+                    if (lane == 0) {
+                        mma_tf32_ss(tmem_base, make_smem_desc(sbase + lay.bias[l], kChunkStrideA, 128),
+                                    make_smem_desc(sbase + lay.ones, kChunkStrideA, 128), idesc, true);  // + bias
+                        mma_commit(bar);
+                    }
                 }
                 __syncwarp();
             }
-            mbar_wait_relaxed(bar, phase);
+            mbar_wait_suspend(bar, phase);
             phase ^= 1;
             tc_fence_after();
 
-            const bool last = (l == p.L - 1);
-            for (int c0 = 0; c0 < np; c0 += 32) {
-                uint32_t v[32];
-                const bool full = np - c0 >= 32;             // np is a multiple of 16: a chunk is 32 or 16 wide
-                if (full) tmem_ld32(tmem_row + c0, v);
-                else tmem_ld16(tmem_row + c0, v);
-                if (!last) {
+            if (!last) {
+                switch (np) {
+                    case 16: mid_epilogue<16>(tmem_row, a_hi, a_lo, r); break;
+                    case 32: mid_epilogue<32>(tmem_row, a_hi, a_lo, r); break;
+                    case 48: mid_epilogue<48>(tmem_row, a_hi, a_lo, r); break;
+                    case 64: mid_epilogue<64>(tmem_row, a_hi, a_lo, r); break;
+                    case 80: mid_epilogue<80>(tmem_row, a_hi, a_lo, r); break;
+                    case 96: mid_epilogue<96>(tmem_row, a_hi, a_lo, r); break;
+                    case 112: mid_epilogue<112>(tmem_row, a_hi, a_lo, r); break;
+                    default: mid_epilogue<128>(tmem_row, a_hi, a_lo, r); break;
+                }
+            } else if ((warp & 3) * 32 < cout_last) {
+                // ---- thread r = output channel; columns = rows of the tile, K per neighbourhood ----------
+                const bool store = r < cout_last;
+                float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset + (store ? r : 0)) * p.S + s0;
+                if (p.K == 16 || p.K == 32 || p.K == 64 || p.K == 128) {
+                    float acc = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (i < 16 || full) {
-                            uint32_t hi[4], lo[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                split_tf32(fmaxf(__uint_as_float(v[i + u]), 0.f), hi[u], lo[u]);
-                            const uint32_t off = static_cast<uint32_t>((c0 + i) >> 2) * kChunkStrideA + r * 16;
-                            st_shared_v4(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
-                            st_shared_v4(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
-                        }
-                    }
-                } else if (lane_max) {
-                    // 32 rows of a neighbourhood (or 2 x 16) are the lanes of this warp: one CREDUX per
-                    // channel gives the warp's partial maximum.  Post-ReLU values are >= 0, so signed-int
-                    // order == float order; rows beyond `rows` contribute 0, the identity.
-                    const int wq = warp & 3;
-                    const float live = r < rows ? 1.f : 0.f;  // x * live: exact for the rows that count, 0 else
-                    if (p.K != 16) {
-                        float* dst = part + wq * np + c0;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (i < 16 || full) {
-                                const float x = fmaxf(__uint_as_float(v[i]), 0.f) * live;
-                                const int mx = __reduce_max_sync(FULL, __float_as_int(x));
-                                if (lane == 0) dst[i] = __int_as_float(mx);
-                            }
-                        }
-                    } else {
-                        float* da = part + (2 * wq) * np + c0;
-                        float* db = part + (2 * wq + 1) * np + c0;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (i < 16 || full) {
-                                const float x = fmaxf(__uint_as_float(v[i]), 0.f) * live;
-                                const int ma = __reduce_max_sync(FULL, lane < 16 ? __float_as_int(x) : 0);
-                                const int mb = __reduce_max_sync(FULL, lane >= 16 ? __float_as_int(x) : 0);
-                                if (lane == 0) { da[i] = __int_as_float(ma); db[i] = __int_as_float(mb); }
+                    for (int q = 0; q < 4; ++q) {
+                        if (32 * q < rows) {                              // tile-uniform
+                            uint32_t v[32];
+                            tmem_ld32(tmem_row + 32 * q, v);
+                            const float m_lo = relu_max16<0>(v), m_hi = relu_max16<16>(v);
+                            if (p.K == 16) {
+                                if (store) {
+                                    ob[2 * q] = m_lo;
+                                    if (2 * q + 1 < groups) ob[2 * q + 1] = m_hi;
+                                }
+                            } else {
+                                acc = max3(acc, m_lo, m_hi);
+                                const int cpn = p.K >> 5;                 // 32-column chunks per neighbourhood
+                                if (((q + 1) & (cpn - 1)) == 0) {
+                                    if (store) ob[q / cpn] = acc;
+                                    acc = 0.f;
+                                }
                             }
                         }
                     }
                 } else {
-                    float* stage = reinterpret_cast<float*>(smem + lay.a_hi[g]);
+                    // any other K <= 128: running maximum over the columns, flushed every K columns
+                    float acc = 0.f;
+                    int cnt = 0, sg = 0;
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        if (32 * q < rows) {
+                            uint32_t v[32];
+                            tmem_ld32(tmem_row + 32 * q, v);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < 16 || full)
-                            stage[r * lay.stage_stride + c0 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
+                            for (int i = 0; i < 32; ++i) {
+                                acc = fmaxf(acc, __uint_as_float(v[i]));
+                                if (++cnt == p.K) {
+                                    if (store && sg < groups) ob[sg] = acc;
+                                    acc = 0.f; cnt = 0; ++sg;
+                                }
+                            }
+                        }
+                    }
                 }
             }
             tc_fence_before();             // TMEM reads done before the next layer's MMAs overwrite D
-        }
-
-        if (lane_max) {
-            // ---- combine the per-warp partial maxima of each neighbourhood, channel-first store -----------
-            group_sync(g);
-            const int np = lay.npad[p.L - 1];
-            const int ppn = p.K == 16 ? 1 : p.K / 32;          // partial rows per neighbourhood
-            float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
-            for (int e = r; e < groups * cout_last; e += kRows) {
-                const int co = e / groups, sg = e - co * groups;
-                float m = part[(sg * ppn) * np + co];
-                for (int q = 1; q < ppn; ++q) m = fmaxf(m, part[(sg * ppn + q) * np + co]);
-                ob[static_cast<size_t>(co) * p.S + s0 + sg] = m;
-            }
-        } else {
-            // ---- generic K: max over the K rows of each neighbourhood through shared memory -------------
-            group_sync(g);
-            const float* stage = reinterpret_cast<const float*>(smem + lay.a_hi[g]);
-            float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
-            for (int e = r; e < groups * cout_last; e += kRows) {
-                const int sg = e / cout_last, co = e - sg * cout_last;
-                float m = stage[(sg * p.K) * lay.stage_stride + co];
-                for (int k = 1; k < p.K; ++k) m = fmaxf(m, stage[(sg * p.K + k) * lay.stage_stride + co]);
-                ob[static_cast<size_t>(co) * p.S + s0 + sg] = m;
-            }
-            group_sync(g);                 // staging area becomes the next tile's A operand
         }
     }
 
@@ -401,7 +452,7 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 bool make_layout(const SaParams& p, TcLayout& lay)
 {
     if (p.K > kRows || p.K < 1) return false;
-    int kmax = 0, nmax = 0, nlast = 0;
+    int kmax = 0;
     uint32_t off = 0;
     auto take = [&off](uint32_t bytes, uint32_t align) {
         off = (off + align - 1) / align * align;
@@ -414,31 +465,27 @@ bool make_layout(const SaParams& p, TcLayout& lay)
         lay.npad[l] = (p.ch[l + 1] + 15) / 16 * 16;
         if (lay.npad[l] > 128 || lay.kpad[l] > 128) return false;
         kmax = std::max(kmax, lay.kpad[l]);
-        nmax = std::max(nmax, lay.npad[l]);
-        nlast = lay.npad[l];
     }
-    lay.stage_stride = nlast + 1;
-    const bool lane_max = (p.K == 16 || p.K == 32 || p.K == 64 || p.K == 128);
     const uint32_t a_bytes = static_cast<uint32_t>(kmax / 4) * kChunkStrideA;
-    const uint32_t stage_bytes = lane_max ? 0u : static_cast<uint32_t>(kRows) * lay.stage_stride * 4;
     for (int g = 0; g < kGroups; ++g) {
-        lay.a_hi[g] = take(std::max(a_bytes, stage_bytes), 128);
+        lay.a_hi[g] = take(a_bytes, 128);
         lay.a_lo[g] = take(a_bytes, 128);
-        lay.part[g] = take(lane_max ? 8u * nlast * 4u : 0u, 16);
     }
     for (int l = 0; l < p.L; ++l) {
-        const uint32_t wb = static_cast<uint32_t>(lay.npad[l]) * lay.kpad[l] * 4;
+        const int rows_w = l == p.L - 1 ? kRows : lay.npad[l];      // the last layer's weights are a 128-row A operand
+        const uint32_t wb = static_cast<uint32_t>(rows_w) * lay.kpad[l] * 4;
         lay.w_hi[l] = take(wb, 128);
         lay.w_lo[l] = take(wb, 128);
-        lay.bias[l] = take(lay.npad[l] * 32, 128);       // [npad x 8] B tile: bias_hi | bias_lo | 0...
+        lay.bias[l] = take(rows_w * 32, 128);            // [rows x 8] tile: bias_hi | bias_lo | 0...
     }
     lay.ones = take(kRows * 32, 128);
     lay.misc = take(8 + 8 * kGroups, 16);
     lay.total = off;
-    lay.group_cols = nmax <= 32 ? 32 : (nmax <= 64 ? 64 : 128);
-    lay.tmem_cols = lay.group_cols * kGroups;          // 128, 256 or 512: a power of two >= 32
+    lay.group_cols = kRows;                            // the transposed last layer fills 128 columns per group
+    lay.tmem_cols = lay.group_cols * kGroups;          // 512: all of tensor memory (one CTA per SM by design)
     lay.gpt = kRows / p.K;
     lay.tiles_per_cloud = (p.S + lay.gpt - 1) / lay.gpt;
+    lay.tpc_magic = static_cast<uint32_t>(std::min<unsigned long long>((1ull << 32) / static_cast<unsigned long long>(lay.tiles_per_cloud), 0xFFFFFFFFull));
     return lay.total <= 220 * 1024;
 }
 
