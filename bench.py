@@ -194,12 +194,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clouds", type=int, default=592, help="clouds per GPU per step (4 per SM)")
+    ap.add_argument("--clouds", type=int, default=1184, help="clouds per GPU per step (8 per SM)")
     ap.add_argument("--cpu-clouds", type=int, default=0, help="clouds in the CPU sample (default: host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=148, help="clouds per pipelined chunk of the end-to-end measurement")
     ap.add_argument("--e2e-streams", type=int, default=4)
-    ap.add_argument("--fps-mode", type=int, default=0, help="0 auto; 100*G+CS forces an FPS kernel shape (experiments)")
+    ap.add_argument("--fps-mode", type=int, default=0, help="0 auto; 100*G+CS resident shape, -2 bucket, -(10+W) bucket with W warps per cloud (experiments)")
     ap.add_argument("--sa-engine", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -435,9 +435,10 @@ int fps_dispatch(int b, int n_max, const float* xyz, const int* offset, const in
     }
     // Auto: small clouds stay register-resident in one CTA (cheapest iteration); everything larger
     // goes to the bucket-pruned kernel, which wins both on latency and on throughput.
-    if (mode == -2 || (mode == 0 && n_max > 4096 && n_max <= fps_bucket_max_points())) {
+    // mode -2: bucket kernel, shape by batch size; mode -(10 + W): bucket kernel with W warps per cloud.
+    if (mode == -2 || (mode <= -11 && mode >= -26) || (mode == 0 && n_max > 4096 && n_max <= fps_bucket_max_points())) {
         if (n_max > fps_bucket_max_points()) { set_error("furthestsampling: n_max=%d exceeds the bucket kernel", n_max); return TGN_ERR_INVALID; }
-        return fps_bucket_launch(b, n_max, xyz, offset, new_offset, tmp, idx, bs_log2, stream);
+        return fps_bucket_launch(b, n_max, xyz, offset, new_offset, tmp, idx, bs_log2, mode <= -11 ? -mode - 10 : 0, stream);
     }
     FpsConfig cfg{0, 0, 0, 0};
     if (mode > 0) {

@@ -4,30 +4,31 @@
 // samples, a new sample only lowers the running minimum of the points NEAR it.  This kernel
 // keeps the reference's result bit for bit and skips the rest:
 //
-//  * prologue kernel: the cloud is sorted by a 21-bit Morton code (stable LSD radix sort, three
-//    7-bit passes, one CTA per cloud) so that every 32 consecutive points -- a BUCKET, exactly one
-//    coalesced 512-byte float4 row -- are spatial neighbours; each bucket gets an axis-aligned
-//    bounding box (inflated by an absolute slack).
-//  * main kernel (one CTA of 16 warps per cloud, several CTAs per SM); warp w OWNS the contiguous
-//    bucket range [w*R, (w+1)*R) and caches its best candidate and the union box of the range.
-//    Per iteration, with o the new sample:
+//  * prologue kernel (one CTA per cloud): the cloud is sorted by a Morton code (stable LSD radix sort;
+//    clouds up to 26.6k points entirely in shared memory on 17-bit codes, larger ones through global
+//    memory on 21-bit codes) so that every 64 consecutive points -- a BUCKET, two points per lane of
+//    a warp -- are spatial neighbours; each bucket gets an axis-aligned bounding box (inflated by an
+//    absolute slack).  Sorted points are stored lane-major as pairs, (x0,x1,y0,y1) and
+//    (z0,z1,key0,key1), so that the distance update runs on the packed fp32x2 pipe.
+//  * main kernel (one CTA of 4, 8 or 16 warps per cloud, 8, 4 or 2 CTAs per SM); warp w OWNS the
+//    contiguous bucket range [w*R, (w+1)*R) and caches its best candidate and the union box of the
+//    range.  Per iteration, with o the new sample:
 //      (a) owner warps test their range box, then their buckets: for every point p of a box,
 //          |p - o|^2 >= dist^2(o, box), so if dist^2(o, box) > max_t(box) * (1 + 2e-5) the update
 //          min(t, |p-o|^2) cannot change any t inside (the slack terms dominate every fp32 rounding
 //          error involved; DESIGN.md "pruning is conservative") and the box is skipped;
-//      (b) surviving buckets are spread over all warps, one warp per bucket, four loads in flight: the
-//          32 points are re-evaluated with the reference's exact arithmetic (FMUL dy*dy,
-//          FFMA dx*dx+., FFMA dz*dz+., FMNMX), changed minima are written back and the bucket's
-//          cached candidate (max t, tie key, coordinates) is refreshed;
+//      (b) surviving buckets are spread over all warps, one warp per bucket, two buckets in flight: the
+//          64 points are re-evaluated with the reference's exact arithmetic (FMUL dy*dy,
+//          FFMA dx*dx+., FFMA dz*dz+., FMNMX; the packed forms round each half identically),
+//          changed minima are written back and the bucket's cached candidate (max t, tie key,
+//          coordinates) is refreshed;
 //      (c) owner warps whose range was touched refresh their range candidate; the block arg-max is
-//          one CREDUX pair over the 16 range candidates.
+//          one CREDUX pair over the range candidates.
 //    Ties are resolved by the reference's order (bitrev(j mod BS), j div BS) on ORIGINAL indices:
-//    that key travels in the w component of each sorted point (j is recovered from it), so the
-//    result does not depend on the internal order.
-//  * the clouds live in L2 (20 B/point), the bucket table in shared memory; an iteration is three
-//    block barriers and one L2 round trip, hidden by the other CTAs of the SM -- a 126 MB L2 holds
-//    ~300 clouds of 24k points at once, which is what makes "one CTA per cloud, several CTAs per SM"
-//    possible on B200.
+//    that key travels with each sorted point (j is recovered from it), so the result does not depend
+//    on the internal order.
+//  * the bucket table lives in shared memory (52 B per bucket), the points in L2/HBM (20 B/point); an
+//    iteration is three block barriers and one memory round trip, hidden by the other CTAs of the SM.
 #include <algorithm>
 #include <climits>
 
@@ -42,24 +43,27 @@ constexpr int kT = 512;            // sort kernel (latency-bound: more warps per
 constexpr int kNW = kT / 32;
 constexpr int kMT = 512;           // main kernel
 constexpr int kMNW = kMT / 32;
-constexpr int kBatch = 4;          // buckets a warp keeps in flight (memory-level parallelism)
-constexpr int kGatherUnroll = 4;   // buckets a sort-kernel warp gathers together
+constexpr int kBP = 64;            // points per bucket: two per lane
+constexpr int kBatch = 2;          // buckets a warp keeps in flight (memory-level parallelism)
+constexpr int kGatherUnroll = 2;   // buckets a sort-kernel warp gathers together
 constexpr int kRadixUnroll = 4;    // radix steps whose loads are issued together
 constexpr int kSmemSortMaxN = 26624; // clouds up to this size are radix-sorted in shared memory (2 x 4 B per point)
-constexpr int kMaxBuckets = 3600;   // 60 B of shared memory per bucket
+constexpr int kMaxBuckets = 3600;   // 52 B of shared memory per bucket
 constexpr unsigned FULL = 0xffffffffu;
 
 struct BucketWs {
-    float4* pts4;     // [b][stride]   sorted (x, y, z, bits(tie key)); pads carry key INT_MAX
-    float* tval;      // [b][stride]   running minima in sorted order; pads -1
-    uint2* key_a;     // [b][stride]   radix ping
-    uint2* key_b;     // [b][stride]   radix pong
-    float4* box_lo;   // [b][nbmax]    inflated box minimum, w = initial max t of the bucket
-    float4* box_hi;   // [b][nbmax]    inflated box maximum
-    int2* bvk;        // [b][nbmax]    initial cached candidate (value bits, tie key)
-    float4* bxyz;     // [b][nbmax]    initial cached candidate coordinates
-    int stride, nbmax;
+    float4* pa;       // [b][stride/2]  bucket-major, lane-major pairs (x0, x1, y0, y1); point 1 is 32 places after point 0
+    float4* pb;       // [b][stride/2]  (z0, z1, bits(key0), bits(key1)); pads carry key INT_MAX
+    float2* tv;       // [b][stride/2]  running minima (t0, t1); pads -1
+    uint2* key_a;     // [b][stride]    radix ping (clouds too large for the shared-memory sort)
+    uint2* key_b;     // [b][stride]    radix pong
+    float4* box_lo;   // [b][nbmax]     inflated box minimum, w = initial max t of the bucket
+    float4* box_hi;   // [b][nbmax]     inflated box maximum, w = bits of that max t
+    float4* bxyz;     // [b][nbmax]     initial cached candidate (x, y, z, bits(key))
+    int stride;       // points per cloud slot (multiple of 64)
+    int nbmax;        // buckets per cloud slot
 };
+
 
 __device__ __forceinline__ int bitrev_low(int v, int bits) {
     return bits ? static_cast<int>(__brev(static_cast<unsigned>(v)) >> (32 - bits)) : 0;
@@ -228,10 +232,11 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
     const int n = offset[cloud] - start_n;
     if (n <= 0) return;
     const float* cx = xyz + 3 * static_cast<size_t>(start_n);
-    float4* pts4 = ws.pts4 + static_cast<size_t>(cloud) * ws.stride;
-    float* tval = ws.tval + static_cast<size_t>(cloud) * ws.stride;
-    uint2* ka = ws.key_a + static_cast<size_t>(cloud) * ws.stride;
-    uint2* kb = ws.key_b + static_cast<size_t>(cloud) * ws.stride;
+    float4* __restrict__ pa = ws.pa + static_cast<size_t>(cloud) * (ws.stride / 2);
+    float4* __restrict__ pb = ws.pb + static_cast<size_t>(cloud) * (ws.stride / 2);
+    float2* __restrict__ tv2 = ws.tv + static_cast<size_t>(cloud) * (ws.stride / 2);
+    uint2* ka = SMEM_ ? nullptr : ws.key_a + static_cast<size_t>(cloud) * ws.stride;
+    uint2* kb = SMEM_ ? nullptr : ws.key_b + static_cast<size_t>(cloud) * ws.stride;
 
     // ---- bounding box --------------------------------------------------------------------------------
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -291,59 +296,71 @@ fps_bucket_sort_kernel(const float* __restrict__ xyz, const int* __restrict__ of
     }
 
     // ---- sorted points, running minima, bucket boxes and initial candidates -------------------------------
-    // A warp writes one bucket (32 consecutive sorted points) per step and reduces its box and best
-    // candidate from the registers it just filled; kGatherUnroll buckets are in flight per warp.
-    const int npad = (n + 31) & ~31;
-    const int nb = npad >> 5;
+    // A warp writes one bucket (64 consecutive sorted points, two per lane) per step and reduces its box
+    // and best candidate from the registers it just filled; kGatherUnroll buckets are in flight per warp.
+    const int nb = (n + kBP - 1) / kBP;
     float4* __restrict__ blo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
     float4* __restrict__ bhi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
-    int2* __restrict__ bvk = ws.bvk + static_cast<size_t>(cloud) * ws.nbmax;
     float4* __restrict__ bxyz = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
     for (int bk0 = warp; bk0 < nb; bk0 += kNW * kGatherUnroll) {
-        int j[kGatherUnroll];
-        float4 P[kGatherUnroll];
-        float tv[kGatherUnroll];
+        int j[kGatherUnroll][2];
+        float x[kGatherUnroll][2], y[kGatherUnroll][2], z[kGatherUnroll][2], t[kGatherUnroll][2];
 #pragma unroll
-        for (int u = 0; u < kGatherUnroll; ++u) {
-            const int p = (bk0 + u * kNW) * 32 + lane;
-            j[u] = p < n ? (SMEM_ ? static_cast<int>(sb[p] & 0x7FFFu) : static_cast<int>(kb[p].y)) : -1;
-        }
+        for (int u = 0; u < kGatherUnroll; ++u)
 #pragma unroll
-        for (int u = 0; u < kGatherUnroll; ++u) {
-            if (j[u] >= 0) {
-                const float* q = cx + 3 * static_cast<size_t>(j[u]);
-                P[u] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __int_as_float(point_key(j[u], bs_log2)));
-                tv[u] = tmp ? __ldg(tmp + start_n + j[u]) : 1e10f;
-            } else {
-                P[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(INT_MAX));
-                tv[u] = -1.0f;
+            for (int h = 0; h < 2; ++h) {
+                const int p = (bk0 + u * kNW) * kBP + 32 * h + lane;
+                j[u][h] = p < n ? (SMEM_ ? static_cast<int>(sb[p] & 0x7FFFu) : static_cast<int>(kb[p].y)) : -1;
             }
-        }
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (j[u][h] >= 0) {
+                    const float* q = cx + 3 * static_cast<size_t>(j[u][h]);
+                    x[u][h] = __ldg(q); y[u][h] = __ldg(q + 1); z[u][h] = __ldg(q + 2);
+                    t[u][h] = tmp ? __ldg(tmp + start_n + j[u][h]) : 1e10f;
+                } else {
+                    x[u][h] = y[u][h] = z[u][h] = 0.f;
+                    t[u][h] = -1.0f;
+                }
+            }
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u) {
             const int bk = bk0 + u * kNW;
             if (bk >= nb) break;                      // warp-uniform
-            pts4[bk * 32 + lane] = P[u];
-            tval[bk * 32 + lane] = tv[u];
-            const bool ok = j[u] >= 0;
-            const float lx = ordered_min(ok ? P[u].x : INFINITY), hx = ordered_max(ok ? P[u].x : -INFINITY);
-            const float ly = ordered_min(ok ? P[u].y : INFINITY), hy = ordered_max(ok ? P[u].y : -INFINITY);
-            const float lz = ordered_min(ok ? P[u].z : INFINITY), hz = ordered_max(ok ? P[u].z : -INFINITY);
-            const int key = __float_as_int(P[u].w);
-            const int bi = __float_as_int(tv[u]);
-            const int wmax = __reduce_max_sync(FULL, bi);
-            const int wkey = __reduce_min_sync(FULL, bi == wmax ? key : INT_MAX);
+            const int k0 = j[u][0] >= 0 ? point_key(j[u][0], bs_log2) : INT_MAX;
+            const int k1 = j[u][1] >= 0 ? point_key(j[u][1], bs_log2) : INT_MAX;
+            pa[bk * 32 + lane] = make_float4(x[u][0], x[u][1], y[u][0], y[u][1]);
+            pb[bk * 32 + lane] = make_float4(z[u][0], z[u][1], __int_as_float(k0), __int_as_float(k1));
+            tv2[bk * 32 + lane] = make_float2(t[u][0], t[u][1]);
+            const bool ok0 = j[u][0] >= 0, ok1 = j[u][1] >= 0;
+            const float lx = ordered_min(fminf(ok0 ? x[u][0] : INFINITY, ok1 ? x[u][1] : INFINITY));
+            const float ly = ordered_min(fminf(ok0 ? y[u][0] : INFINITY, ok1 ? y[u][1] : INFINITY));
+            const float lz = ordered_min(fminf(ok0 ? z[u][0] : INFINITY, ok1 ? z[u][1] : INFINITY));
+            const float hx = ordered_max(fmaxf(ok0 ? x[u][0] : -INFINITY, ok1 ? x[u][1] : -INFINITY));
+            const float hy = ordered_max(fmaxf(ok0 ? y[u][0] : -INFINITY, ok1 ? y[u][1] : -INFINITY));
+            const float hz = ordered_max(fmaxf(ok0 ? z[u][0] : -INFINITY, ok1 ? z[u][1] : -INFINITY));
+            const int b0 = __float_as_int(t[u][0]), b1 = __float_as_int(t[u][1]);
+            const bool take1 = b1 > b0 || (b1 == b0 && k1 < k0);
+            const int bl = take1 ? b1 : b0, kl = take1 ? k1 : k0;
+            const int wmax = __reduce_max_sync(FULL, bl);
+            const int wkey = __reduce_min_sync(FULL, bl == wmax ? kl : INT_MAX);
             if (lane == 0) {
                 blo[bk] = make_float4(lx - slack, ly - slack, lz - slack, __int_as_float(wmax));
-                bhi[bk] = make_float4(hx + slack, hy + slack, hz + slack, 0.f);
+                bhi[bk] = make_float4(hx + slack, hy + slack, hz + slack, __int_as_float(wmax));
             }
-            if (bi == wmax && key == wkey) { bvk[bk] = make_int2(wmax, wkey); bxyz[bk] = P[u]; }
+            if (bl == wmax && kl == wkey)
+                bxyz[bk] = make_float4(take1 ? x[u][1] : x[u][0], take1 ? y[u][1] : y[u][0], take1 ? z[u][1] : z[u][0],
+                                       __int_as_float(wkey));
         }
     }
 }
 
 // MT_ = 512: 16 warps per cloud, 2 clouds per SM (shortest iteration; batches up to 2 clouds per SM).
-// MT_ = 256:  8 warps per cloud, 4 clouds per SM (more clouds in flight hide the barriers of large batches).
+// MT_ = 256:  8 warps per cloud, 4 clouds per SM.
+// MT_ = 128:  4 warps per cloud, 8 clouds per SM (least per-warp overhead per cloud, most clouds in flight to
+//             hide the barriers and the memory round trip: the throughput shape for large batches).
 // Either way <= 64 registers per thread.
 template <int MT_>
 __global__ void __launch_bounds__(MT_, 1024 / MT_)
@@ -365,15 +382,15 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     if (tid == 0) idx[start_m] = start_n;                      // sampling_cuda_kernel.cu:39
     if (m == 1) return;
 
-    const int nb = ((n + 31) & ~31) >> 5;
+    const int nb = (n + kBP - 1) / kBP;
     float4* blo = reinterpret_cast<float4*>(dyn);                                   // [nbmax] box min, w = skip threshold
-    float4* bhi = blo + ws.nbmax;                                                   // [nbmax] box max
+    float4* bhi = blo + ws.nbmax;                                                   // [nbmax] box max, w = candidate value bits
     float4* cxyz = bhi + ws.nbmax;                                                  // [nbmax] candidate x,y,z,key bits
-    int2* cvk = reinterpret_cast<int2*>(cxyz + ws.nbmax);                           // [nbmax] candidate value bits, key
-    int* alist = reinterpret_cast<int*>(cvk + ws.nbmax);                            // [nbmax] active buckets
+    int* alist = reinterpret_cast<int*>(cxyz + ws.nbmax);                           // [nbmax] active buckets
 
-    const float4* pts4 = ws.pts4 + static_cast<size_t>(cloud) * ws.stride;
-    float* tval = ws.tval + static_cast<size_t>(cloud) * ws.stride;
+    const float4* __restrict__ pa = ws.pa + static_cast<size_t>(cloud) * (ws.stride / 2);
+    const float4* __restrict__ pb = ws.pb + static_cast<size_t>(cloud) * (ws.stride / 2);
+    float2* tv2 = ws.tv + static_cast<size_t>(cloud) * (ws.stride / 2);
 
     // ---- owner ranges: warp w owns buckets [r0, r1); lane l looks after r0 + l, r0 + l + 32, ... -------------
     const int per = (nb + kMNW - 1) / kMNW;
@@ -381,12 +398,11 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     {
         const float4* glo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
         const float4* ghi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
-        const int2* gv = ws.bvk + static_cast<size_t>(cloud) * ws.nbmax;
         const float4* gx = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
         for (int bk = tid; bk < nb; bk += kMT) {
             float4 lo = glo[bk];
             lo.w = skip_threshold(lo.w);                     // w held the bucket's initial max t
-            blo[bk] = lo; bhi[bk] = ghi[bk]; cvk[bk] = gv[bk]; cxyz[bk] = gx[bk];
+            blo[bk] = lo; bhi[bk] = ghi[bk]; cxyz[bk] = gx[bk];
         }
         if (tid == 0) nact = 0;
     }
@@ -404,8 +420,8 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     auto refresh_range = [&]() {          // best candidate over the owned buckets -> wres[warp]
         int bv = INT_MIN, bkey = INT_MAX, bbk = r0;
         for (int bk = r0 + lane; bk < r1; bk += 32) {
-            const int2 c = cvk[bk];
-            if (c.x > bv || (c.x == bv && c.y < bkey)) { bv = c.x; bkey = c.y; bbk = bk; }
+            const int v = __float_as_int(bhi[bk].w), k = __float_as_int(cxyz[bk].w);
+            if (v > bv || (v == bv && k < bkey)) { bv = v; bkey = k; bbk = bk; }
         }
         const int wv = __reduce_max_sync(FULL, bv);
         const int wk = __reduce_min_sync(FULL, bv == wv ? bkey : INT_MAX);
@@ -442,43 +458,52 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
         __syncthreads();
         const int na = nact;
 
-        // ---- (b) exact update of the surviving buckets: one warp per bucket, kBatch loads in flight ---------
+        // ---- (b) exact update of the surviving buckets: one warp per bucket, kBatch buckets in flight ---------
+        const uint64_t ox2 = pack2(ox, ox), oy2 = pack2(oy, oy), oz2 = pack2(oz, oz);
         for (int a0 = warp; a0 < na; a0 += kMNW * kBatch) {
             int bk[kBatch];
-            float4 P[kBatch];
-            float tv[kBatch];
+            float4 A[kBatch], B[kBatch];
+            float2 T[kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const int a = a0 + u * kMNW;
                 bk[u] = a < na ? alist[a] : -1;
                 if (bk[u] >= 0) {
-                    P[u] = __ldg(pts4 + bk[u] * 32 + lane);
-                    tv[u] = __ldcg(tval + bk[u] * 32 + lane);
+                    A[u] = __ldg(pa + bk[u] * 32 + lane);
+                    B[u] = __ldg(pb + bk[u] * 32 + lane);
+                    T[u] = __ldcg(tv2 + bk[u] * 32 + lane);
                 }
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                if (bk[u] < 0) continue;                      // warp-uniform
-                const float dx = P[u].x - ox, dy = P[u].y - oy, dz = P[u].z - oz;
-                float d = __fmul_rn(dy, dy);
-                d = __fmaf_rn(dx, dx, d);
-                d = __fmaf_rn(dz, dz, d);
-                const float nt = fminf(d, tv[u]);
-                if (nt < tv[u]) __stcg(tval + bk[u] * 32 + lane, nt);
-                const int bi = __float_as_int(nt);          // pads stay at -1
-                const int wmax = __reduce_max_sync(FULL, bi);
-                const int wkey = __reduce_min_sync(FULL, bi == wmax ? __float_as_int(P[u].w) : INT_MAX);
-                if (bi == wmax && __float_as_int(P[u].w) == wkey) {
-                    cvk[bk[u]] = make_int2(wmax, wkey);
-                    cxyz[bk[u]] = P[u];
-                    blo[bk[u]].w = skip_threshold(nt);
+                if (bk[u] < 0) break;                         // warp-uniform
+                const uint64_t dx = sub2(pack2(A[u].x, A[u].y), ox2), dy = sub2(pack2(A[u].z, A[u].w), oy2),
+                               dz = sub2(pack2(B[u].x, B[u].y), oz2);
+                uint64_t d = mul2(dy, dy);
+                d = fma2(dx, dx, d);
+                d = fma2(dz, dz, d);
+                float d0, d1;
+                unpack2(d, d0, d1);
+                const float n0 = fminf(d0, T[u].x), n1 = fminf(d1, T[u].y);
+                if (n0 < T[u].x || n1 < T[u].y) __stcg(tv2 + bk[u] * 32 + lane, make_float2(n0, n1));
+                const int b0 = __float_as_int(n0), b1 = __float_as_int(n1);          // pads stay at -1
+                const int k0 = __float_as_int(B[u].z), k1 = __float_as_int(B[u].w);
+                const bool take1 = b1 > b0 || (b1 == b0 && k1 < k0);
+                const int bl = take1 ? b1 : b0, kl = take1 ? k1 : k0;
+                const int wmax = __reduce_max_sync(FULL, bl);
+                const int wkey = __reduce_min_sync(FULL, bl == wmax ? kl : INT_MAX);
+                if (bl == wmax && kl == wkey) {
+                    cxyz[bk[u]] = make_float4(take1 ? A[u].y : A[u].x, take1 ? A[u].w : A[u].z, take1 ? B[u].y : B[u].x,
+                                              __int_as_float(wkey));
+                    bhi[bk[u]].w = __int_as_float(wmax);
+                    blo[bk[u]].w = skip_threshold(__int_as_float(wmax));
                 }
             }
         }
         __syncthreads();
         if (tid == 0) nact = 0;
 
-        // ---- (c) touched ranges refresh their candidate; block arg-max over the 16 range candidates ------------
+        // ---- (c) touched ranges refresh their candidate; block arg-max over the range candidates ---------------
         if (dirty) range_thr = skip_threshold(__int_as_float(refresh_range()));
         __syncthreads();
         {
@@ -496,45 +521,61 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
 
     if (tmp) {
         __syncthreads();
-        for (int p = tid; p < n; p += kMT) {
-            const int j = key_to_index(__float_as_int(__ldg(&pts4[p].w)), bs_log2);
-            tmp[start_n + j] = __ldcg(tval + p);
+        for (int q = tid; q < nb * 32; q += kMT) {           // q = bucket * 32 + lane
+            const float4 B = __ldg(pb + q);
+            const float2 T = __ldcg(tv2 + q);
+            const int k0 = __float_as_int(B.z), k1 = __float_as_int(B.w);
+            if (k0 != INT_MAX) tmp[start_n + key_to_index(k0, bs_log2)] = T.x;
+            if (k1 != INT_MAX) tmp[start_n + key_to_index(k1, bs_log2)] = T.y;
         }
     }
 }
 
-bool g_pool_configured = false;
+template <int MT_>
+int launch_main(int b, size_t smem, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
+                const BucketWs& ws, int bs_log2, cudaStream_t stream)
+{
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        const cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
+        configured = smem;
+    }
+    fps_bucket_kernel<MT_><<<b, MT_, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
+    return check_launch("fps_bucket_kernel");
+}
 
 }  // namespace
 
 // Largest cloud the bucket kernel takes (the bucket table must fit in shared memory).
-int fps_bucket_max_points() { return kMaxBuckets * 32; }
+int fps_bucket_max_points() { return kMaxBuckets * kBP; }
 
 int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
-                      int bs_log2, cudaStream_t stream)
+                      int bs_log2, int shape, cudaStream_t stream)
 {
     BucketWs ws{};
-    ws.stride = (n_max + 31) & ~31;
-    ws.nbmax = ws.stride / 32;
+    ws.stride = (n_max + kBP - 1) / kBP * kBP;
+    ws.nbmax = ws.stride / kBP;
+    const bool smem_sort = n_max <= kSmemSortMaxN;
     const size_t pts = static_cast<size_t>(b) * ws.stride;
     const size_t nbt = static_cast<size_t>(b) * ws.nbmax;
     // one stream-ordered allocation, carved
     size_t off = 0;
     auto take = [&off](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~static_cast<size_t>(255); return o; };
-    const size_t o_pts = take(pts * sizeof(float4)), o_t = take(pts * sizeof(float)), o_ka = take(pts * sizeof(uint2)),
-                 o_kb = take(pts * sizeof(uint2)), o_lo = take(nbt * sizeof(float4)), o_hi = take(nbt * sizeof(float4)),
-                 o_bv = take(nbt * sizeof(int2)), o_bx = take(nbt * sizeof(float4));
+    const size_t o_pa = take(pts / 2 * sizeof(float4)), o_pb = take(pts / 2 * sizeof(float4)), o_t = take(pts / 2 * sizeof(float2)),
+                 o_ka = take(smem_sort ? 0 : pts * sizeof(uint2)), o_kb = take(smem_sort ? 0 : pts * sizeof(uint2)),
+                 o_lo = take(nbt * sizeof(float4)), o_hi = take(nbt * sizeof(float4)), o_bx = take(nbt * sizeof(float4));
     keep_async_pool();
     unsigned char* base = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&base), off, stream);
     if (e != cudaSuccess) { set_error("furthestsampling: workspace of %zu bytes: %s", off, cudaGetErrorString(e)); (void)cudaGetLastError(); return TGN_ERR_CUDA; }
-    ws.pts4 = reinterpret_cast<float4*>(base + o_pts);
-    ws.tval = reinterpret_cast<float*>(base + o_t);
+    ws.pa = reinterpret_cast<float4*>(base + o_pa);
+    ws.pb = reinterpret_cast<float4*>(base + o_pb);
+    ws.tv = reinterpret_cast<float2*>(base + o_t);
     ws.key_a = reinterpret_cast<uint2*>(base + o_ka);
     ws.key_b = reinterpret_cast<uint2*>(base + o_kb);
     ws.box_lo = reinterpret_cast<float4*>(base + o_lo);
     ws.box_hi = reinterpret_cast<float4*>(base + o_hi);
-    ws.bvk = reinterpret_cast<int2*>(base + o_bv);
     ws.bxyz = reinterpret_cast<float4*>(base + o_bx);
 
     if (n_max <= kSmemSortMaxN) {
@@ -552,21 +593,20 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     }
     int rc = check_launch("fps_bucket_sort_kernel");
     if (rc == TGN_OK) {
-        const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 3 + sizeof(int2) + sizeof(int));
-        // more than two clouds per SM: narrower CTAs, four clouds per SM in flight
-        const bool narrow = b > 2 * sm_count() && 4 * smem <= 200 * 1024;
-        static size_t configured_wide = 0, configured_narrow = 0;
-        size_t& configured = narrow ? configured_narrow : configured_wide;
-        if (smem > 48 * 1024 && smem > configured) {
-            e = narrow ? cudaFuncSetAttribute(fps_bucket_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                       : cudaFuncSetAttribute(fps_bucket_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = TGN_ERR_CUDA; }
-            else configured = smem;
-        }
-        if (rc == TGN_OK) {
-            if (narrow) fps_bucket_kernel<256><<<b, 256, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
-            else fps_bucket_kernel<512><<<b, 512, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
-            rc = check_launch("fps_bucket_kernel");
+        const size_t smem = static_cast<size_t>(ws.nbmax) * (sizeof(float4) * 3 + sizeof(int));
+        // Warps per cloud by batch size: the more clouds per SM are available, the narrower the CTA (fewer
+        // redundant per-warp steps and cheaper barriers per cloud, more clouds in flight to hide latency).
+        const int sms = sm_count();
+        auto fits = [&](int per_sm) { return static_cast<size_t>(per_sm) * (smem + 1024) <= 220 * 1024; };
+        int warps = shape;
+        if (warps == 0) warps = (b > 4 * sms && fits(8)) ? 4 : (b > 2 * sms && fits(4)) ? 8 : 16;
+        switch (warps) {
+            case 16: rc = launch_main<512>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+            case 8: rc = launch_main<256>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+            case 4: rc = launch_main<128>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+            case 2: rc = launch_main<64>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+            case 1: rc = launch_main<32>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+            default: set_error("furthestsampling: bucket kernel has no shape of %d warps per cloud", warps); rc = TGN_ERR_INVALID;
         }
     }
     (void)cudaFreeAsync(base, stream);
