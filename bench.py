@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=148, help="clouds per pipelined chunk of the end-to-end measurement")
     ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--fps-mode", type=int, default=0, help="0 auto; 100*G+CS resident shape, -2 bucket, -(10+W) bucket with W warps per cloud (experiments)")
+    ap.add_argument("--ball-path", type=int, default=0, help="0 auto, 4 index-order tile scan, 8 uniform grid (experiments)")
     ap.add_argument("--sa-engine", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -238,6 +239,7 @@ def main():
 
     sa = build_module(device)
     pn2.set_sa_engine(args.sa_engine)
+    pn2.set_ball_path(args.ball_path)
     B = args.clouds
     host_feats = make_clouds(rank, B).pin_memory()
     feats = host_feats.to(device)

@@ -76,10 +76,13 @@ int tgn_launch_count(void);                /* kernels launched by this library i
 
 /* FPS.  Same contract as furthestsampling_cuda_launcher; tmp may be NULL (running minima start
  * at 1e10 and are not written back) when the cloud fits the register-resident kernel.
- * `mode`: 0 = choose by b and n (two clouds software-pipelined per cluster when the batch can
- *         fill the machine, one cloud on a wide cluster when only a few are in flight),
- *         -1 = streaming kernel, otherwise 100*G + CS forces a cluster of CS CTAs (1,2,4,8) with
- *         G clouds in flight (1 or 2; G omitted = 1). */
+ * `mode`: 0 = choose by b and n_max: clouds of more than 4096 points go to the bucket-pruned kernel
+ *         (Morton-sorted 64-point buckets, exact; 16, 8 or 4 warps per cloud as the batch grows),
+ *         smaller ones stay register-resident in one CTA / cluster;
+ *         -1 = streaming kernel (needs tmp); -2 = bucket kernel, shape by batch size;
+ *         -(10 + W) = bucket kernel with W in {16, 8, 4, 2, 1} warps per cloud;
+ *         100*G + CS = register-resident cluster of CS CTAs (1,2,4,8) with G clouds in flight
+ *         (1 or 2; G omitted = 1).  Every mode returns the same indices. */
 int tgn_furthestsampling(int b, int n_max, const float *xyz, const int *offset, const int *new_offset,
                          float *tmp, int *idx, int mode, void *stream);
 
@@ -103,8 +106,10 @@ int tgn_aggregation_backward(int n, int nsample, int c, int w_c, const float *in
  * xyz (B,N,3), new_xyz (B,S,3) -> group_idx (B,S,nsample): the first nsample point indices in
  * ascending order whose EXPANDED squared distance (-2ab + |a|^2 + |b|^2, evaluated in the
  * reference's rounding order) is not > r2, padded with the first hit; N in every slot when the
- * ball is empty.  r2 must be float32(radius**2).  idx64 != 0 writes int64 (the reference's
- * dtype), else int32. */
+ * ball is empty.  r2 must be float32(radius**2).  idx64 is a bit set: bit 0 writes int64 (the
+ * reference's dtype) instead of int32; by default clouds of >= 8192 points whose balls are sparse
+ * are answered by a uniform-grid kernel and the rest by an index-order tile scan (same result);
+ * bit 2 (4) forces the tile scan, bit 3 (8) the grid, bit 1 (2) a streaming scan (experiments). */
 int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float *xyz, const float *new_xyz,
                    void *group_idx, int idx64, void *stream);
 

@@ -78,6 +78,38 @@ def test_ball_query_matches_oracle_full_size(N, S, r, K):
     assert np.array_equal(got32.cpu().numpy().astype(np.int64), want)
 
 
+GRID_CASES = [
+    # (N, S, r, K, offset, scale)   every case through BOTH kernels, forced
+    (24000, 1024, 0.1, 32, 0.0, 1.0),       # bench shape: sparse balls
+    (24000, 512, 0.4, 32, 0.0, 1.0),        # dense balls (the estimate would pick the tile kernel)
+    (24000, 512, 0.01, 16, 0.0, 1.0),       # mostly empty / tiny balls, padding with the first member
+    (9000, 300, 0.1, 64, 40.0, 1.0),        # cloud far from the origin: the expanded form is noisy, members far outside r
+    (9000, 300, 2.0, 32, 0.0, 25.0),        # millimetre-like coordinates
+    (1000, 64, 0.15, 8, 0.0, 1.0),          # small cloud (grid only when forced)
+    (70000, 256, 0.05, 32, 0.0, 1.0),       # large cloud, many bitmap words per lane
+    (5000, 100, 5.0, 32, 0.0, 1.0),         # radius larger than the cloud: one cell
+]
+
+
+@pytest.mark.parametrize("N,S,r,K,offset,scale", GRID_CASES)
+def test_ball_query_grid_and_tile_kernels_match_oracle(N, S, r, K, offset, scale):
+    xs = [clouds.dental_arch(N, s)[0] * scale + offset for s in (4, 5)]
+    g = torch.Generator().manual_seed(N + S)
+    news = []
+    for x in xs:
+        q = x[torch.randperm(N, generator=g)[:S]].clone()
+        q[: S // 8] += (torch.rand(S // 8, 3, generator=g) - 0.5) * 4 * r        # queries off the surface
+        q[0] = x.max(0).values + 3 * r + 1.0                                     # outside the bounding box: empty ball
+        news.append(q)
+    xyz, new = torch.stack(xs).contiguous(), torch.stack(news).contiguous()
+    want = oracle.query_ball_point(r, K, xyz.numpy(), new.numpy())
+    for path in (pn2.BALL_GRID, pn2.BALL_TILE, pn2.BALL_AUTO):
+        got = pn2._ball_query(r, K, xyz.cuda(), new.cuda(), True, path)
+        assert np.array_equal(got.cpu().numpy(), want), f"path {path}"
+    got32 = pn2._ball_query(r, K, xyz.cuda(), new.cuda(), False, pn2.BALL_GRID)
+    assert np.array_equal(got32.cpu().numpy().astype(np.int64), want)
+
+
 def test_ball_query_agrees_with_torch_reference_formula_on_device():
     """The reference's own formulation (square_distance + mask + sort) evaluated by torch ON THE
     GPU (cuBLAS fp32, TF32 off): membership must agree pair for pair with the kernel."""

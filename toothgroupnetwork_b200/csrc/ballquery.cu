@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <climits>
 
+#include "ballquery.cuh"
 #include "common.cuh"
 #include "tgn_b200.h"
 
@@ -67,9 +68,10 @@ __device__ __forceinline__ uint64_t lds_f32x2(uint32_t addr) {      // two adjac
 template <int WARPS, typename IdxT>
 __global__ void __launch_bounds__(WARPS * 32)
 ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
-                  IdxT* __restrict__ group_idx)
+                  IdxT* __restrict__ group_idx, const int* __restrict__ answered)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    if (answered && answered[blockIdx.y]) return;     // this cloud went through the grid kernel
     __shared__ __align__(16) float sx[kTile], sy[kTile], sz[kTile], sn[kTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -299,18 +301,46 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
         }
         (void)cudaGetLastError();     // no scratch: fall through to the shared-memory tile kernel
     }
+    // Sparse balls on large clouds: uniform-grid kernel (ballquery_grid.cu); it decides per cloud and
+    // leaves the dense ones to the tile kernel below.  idx64 bit 2 keeps everything on the tile kernel,
+    // bit 3 sends everything through the grid (experiments / tests).
+    const int* answered = nullptr;
+    unsigned char* grid_ws = nullptr;
+    if (!(idx64 & 4) && N <= bq_grid_max_points() && (N >= 8192 || (idx64 & 8))) {
+        keep_async_pool();
+        BqGridWs ws{};
+        const size_t bytes = bq_grid_workspace_bytes(B, N, &ws);
+        if (cudaMallocAsync(reinterpret_cast<void**>(&grid_ws), bytes, st) == cudaSuccess) {
+            ws.ga = reinterpret_cast<float4*>(grid_ws + reinterpret_cast<size_t>(ws.ga));
+            ws.gb = reinterpret_cast<float4*>(grid_ws + reinterpret_cast<size_t>(ws.gb));
+            ws.gj = reinterpret_cast<int2*>(grid_ws + reinterpret_cast<size_t>(ws.gj));
+            ws.cell_start = reinterpret_cast<int*>(grid_ws + reinterpret_cast<size_t>(ws.cell_start));
+            ws.org = reinterpret_cast<float4*>(grid_ws + reinterpret_cast<size_t>(ws.org));
+            ws.dim = reinterpret_cast<int4*>(grid_ws + reinterpret_cast<size_t>(ws.dim));
+            ws.bnd = reinterpret_cast<float4*>(grid_ws + reinterpret_cast<size_t>(ws.bnd));
+            ws.flag = reinterpret_cast<int*>(grid_ws + reinterpret_cast<size_t>(ws.flag));
+            const int rc = bq_grid_launch(B, N, S, r2, nsample, xyz, new_xyz, group_idx, (idx64 & 1) != 0, (idx64 & 8) ? 1 : 0, ws, st);
+            if (rc != TGN_OK) { (void)cudaFreeAsync(grid_ws, st); return rc; }
+            answered = ws.flag;
+        } else {
+            (void)cudaGetLastError();     // no scratch: the tile kernel answers everything
+            grid_ws = nullptr;
+        }
+    }
     // 16 queries per CTA when that still gives >= 2 waves, else 8 (small batches)
     const bool wide = static_cast<long long>(B) * ((S + 15) / 16) >= 2LL * sm_count();
     if (wide) {
         dim3 grid((S + 15) / 16, B);
-        if (idx64 & 1) ball_query_kernel<16, long long><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
-        else ball_query_kernel<16, int><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx));
+        if (idx64 & 1) ball_query_kernel<16, long long><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx), answered);
+        else ball_query_kernel<16, int><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx), answered);
     } else {
         dim3 grid((S + 7) / 8, B);
-        if (idx64 & 1) ball_query_kernel<8, long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx));
-        else ball_query_kernel<8, int><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx));
+        if (idx64 & 1) ball_query_kernel<8, long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx), answered);
+        else ball_query_kernel<8, int><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx), answered);
     }
-    return check_launch("ball_query_kernel");
+    const int rc = check_launch("ball_query_kernel");
+    if (grid_ws) (void)cudaFreeAsync(grid_ws, st);
+    return rc;
 }
 
 int tgn_three_nn(int B, int N, int S, const float* xyz1, const float* xyz2, float* dist, int* idx, void* stream)

@@ -171,12 +171,26 @@ def _radius_sq_f32(radius: float) -> float:
     return float(np.float32(float(radius) ** 2))
 
 
-def _ball_query(radius, nsample, xyz_t, new_xyz_t, idx64: bool) -> torch.Tensor:
+BALL_AUTO, BALL_TILE, BALL_GRID = 0, 4, 8     # kernel choice bits of tgn_ball_query's idx64 argument
+
+
+_ball_path = BALL_AUTO
+
+
+def set_ball_path(path: int) -> None:
+    """Default kernel choice of the ball query (BALL_AUTO / BALL_TILE / BALL_GRID); experiments."""
+    global _ball_path
+    _ball_path = int(path)
+
+
+def _ball_query(radius, nsample, xyz_t, new_xyz_t, idx64: bool, path: int = None) -> torch.Tensor:
+    """``path``: BALL_AUTO lets the library pick per cloud (uniform grid for sparse balls on large
+    clouds, index-order tile scan otherwise); BALL_TILE / BALL_GRID force one kernel (tests)."""
     B, N, _ = xyz_t.shape
     S = new_xyz_t.shape[1]
     out = torch.empty((B, S, nsample), dtype=torch.int64 if idx64 else torch.int32, device=xyz_t.device)
     L.call("tgn_ball_query", B, N, S, ctypes.c_float(_radius_sq_f32(radius)), int(nsample), L.ptr(xyz_t), L.ptr(new_xyz_t),
-           L.ptr(out), 1 if idx64 else 0, L.stream_ptr())
+           L.ptr(out), (1 if idx64 else 0) | int(_ball_path if path is None else path), L.stream_ptr())
     return out
 
 
