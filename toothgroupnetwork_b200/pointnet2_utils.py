@@ -140,8 +140,30 @@ def _take_rows(packed: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _fps_batched(xyz_t: torch.Tensor, npoint: int, mode: int = 0) -> torch.Tensor:
+_fps_mode = 0
+
+
+def set_fps_mode(mode: int) -> None:
+    """Default ``mode`` of tgn_furthestsampling for the pointnet2-side callers (0 = by batch size).
+    A pipeline that keeps several chunks in flight passes -(10 + W) to pick the CTA shape that
+    suits the clouds resident on the GPU rather than the clouds of one call."""
+    global _fps_mode
+    _fps_mode = int(mode)
+
+
+def fps_mode_for_clouds_in_flight(clouds: int, n_points: int) -> int:
+    """The bucket kernel's own rule (fps_bucket.cu: 16 / 8 / 4 warps per cloud at <= 2 / <= 4 / more
+    clouds per SM), applied to a cloud count the caller knows better than a single call does."""
+    if n_points <= 4096:
+        return 0
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return -(10 + (4 if clouds > 4 * sms else (8 if clouds > 2 * sms else 16)))
+
+
+def _fps_batched(xyz_t: torch.Tensor, npoint: int, mode: int = None) -> torch.Tensor:
     """xyz_t (B,N,3) contiguous -> GLOBAL int32 row ids (B*npoint,) of the packed (B*N,3) view."""
+    if mode is None:
+        mode = _fps_mode
     B, N, _ = xyz_t.shape
     dev = xyz_t.device
     offset = torch.arange(1, B + 1, device=dev, dtype=torch.int32) * N
