@@ -18,7 +18,10 @@
 //     K-step issues three kind::tf32 MMAs (hi*hi + lo*hi + hi*lo) into the same accumulator
 //     ("3xTF32"), so the result carries ~2^-21 relative error instead of tf32's 2^-10 -- the
 //     reference's own default for these 1x1 convolutions is plain TF32;
-//   * one elected thread per group issues the MMAs and tcgen05.commit's the group's mbarrier;
+//   * one elected thread per group issues the MMAs and tcgen05.commit's the group's mbarrier (one
+//     completion per barrier between two waits of any thread: a waiter that could see TWO completions
+//     of the same barrier -- tried: the last layer split in two committed halves -- aliases the phase
+//     parity and deadlocks; the split also cost 15 % through the doubled MMA issue);
 //   * the LAST layer runs transposed, D^T[channel, row] = W[channel, K] * X[row, K]^T: the weights
 //     (zero-padded to 128 channels) are the A operand and the activation tile -- already in the
 //     canonical K-major layout -- is the B operand (N = 128 rows).  A TMEM lane is then an output
