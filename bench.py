@@ -18,7 +18,7 @@ metric = sampled points per second = clouds * 1024 / time, whole job (all ranks)
   CUDA-event time inside the timed region, against the measured HBM copy peak.
 * ``cpu_baseline`` / ``--impl reference``: the oracle's port of the reference's CPU-capable
   formulation of the same path, timed on the host cores on a bounded sample of the workload.
-Inputs are larger than L2 (B*24000*6*4 bytes = 341 MB at the default B = 592); no explicit flush.
+Inputs are larger than L2 (B*24000*6*4 bytes = 682 MB at the default B = 1184); no explicit flush.
 """
 from __future__ import annotations
 
@@ -40,9 +40,9 @@ MLP = [32, 32, 64]
 METRIC = "sampled-points/sec (FPS+ballq+group-MLP, 24k-pt cloud)"
 UNIT = "sampled points/s"
 WORKLOAD = "pointnet++ SA1 forward: FPS 24000->1024, ball query r=0.1 K=32, group-MLP 9->[32,32,64], eval BN"
-# dram__bytes_read.sum + dram__bytes_write.sum of fps_bucket_sort_kernel + fps_bucket_kernel<256> in one
-# `ncu --set full` capture of this bench at 592 clouds (profiles/r1c_ncu_full_raw.csv): 7.42 GB per launch pair
-NCU_FPS_DRAM_BYTES_PER_CLOUD = (4.689534e9 + 0.497730e9 + 1.350417e9 + 0.885668e9) / 592
+# dram__bytes_read.sum + dram__bytes_write.sum of fps_bucket_sort_kernel<1> + fps_bucket_kernel<128> in one
+# `ncu --set full` capture of this bench at 1184 clouds (profiles/r1d_ncu_full_raw.csv): 18.12 GB per launch pair
+NCU_FPS_DRAM_BYTES_PER_CLOUD = (16.000872e9 + 1.228595e9 + 0.353967e9 + 0.538954e9) / 1184
 
 
 def host_cores() -> int:
@@ -338,9 +338,11 @@ def main():
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": NCU_FPS_DRAM_BYTES_PER_CLOUD * B, "peak_kind": peak_kind,
                      "dram_achieved_gbs": NCU_FPS_DRAM_BYTES_PER_CLOUD * B / (fps_ms * 1e-3) / 1e9,
+                     "dram_frac": NCU_FPS_DRAM_BYTES_PER_CLOUD * B / (fps_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "note": "achieved = algorithmic 20*(M-1)*N*B bytes / FPS time; frac > 1 because the exact "
-                             "bucket pruning never touches ~97% of those point-updates (profiles/r1_summary.md). "
-                             "traffic = ncu dram read+write of the same launches (profiles/r1c_ncu_full_raw.csv), scaled per cloud"},
+                             "bucket pruning never touches ~97% of those point-updates (profiles/r1_summary.md); dram_frac is the "
+                             "share of the measured HBM peak the kernel's real (random, 1.3 KB-granular) traffic reaches. "
+                             "traffic = ncu dram read+write of the same launches (profiles/r1d_ncu_full_raw.csv), scaled per cloud"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_feats.numel() * 4),
                 "d2h_bytes_per_step": int((out_xyz_host.numel() + out_pts_host.numel()) * 4)},
         "gpu_launches": int(agg["launches"]),
