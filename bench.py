@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=148, help="clouds per pipelined chunk of the end-to-end measurement")
     ap.add_argument("--e2e-streams", type=int, default=2)
+    ap.add_argument("--e2e-groups", default="1", help="chunks per compute group of the end-to-end pipeline")
     ap.add_argument("--fps-mode", type=int, default=0, help="0 auto; 100*G+CS resident shape, -2 bucket, -(10+W) bucket with W warps per cloud (experiments)")
     ap.add_argument("--ball-path", type=int, default=0, help="0 auto, 4 index-order tile scan, 8 uniform grid (experiments)")
     ap.add_argument("--sa-engine", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 (experiments)")
@@ -297,7 +298,8 @@ def main():
     out_pts_host = torch.empty((B, MLP[-1], NPOINT), dtype=torch.float32).pin_memory()
 
     from toothgroupnetwork_b200.pipeline import HostPipeline
-    pipe = HostPipeline(sa, chunk_clouds=args.e2e_chunk, n_streams=args.e2e_streams)
+    pipe = HostPipeline(sa, chunk_clouds=args.e2e_chunk, n_streams=args.e2e_streams,
+                        groups=[int(g) for g in args.e2e_groups.split(",")])
 
     def e2e_step():
         # public API on host buffers: chunks of the batch go H2D -> module.forward -> D2H on a few

@@ -2,8 +2,8 @@
 
 The operators launch on the *current* CUDA stream (and the FPS workspace is stream-ordered), so a
 batch that lives in pinned host memory can be processed in chunks: the H2D copies of all chunks are
-queued back to back on a copy stream, each chunk computes on one of a few compute streams as soon
-as it has landed, and results return on a third stream (PCIe is full duplex).
+queued back to back on a copy stream, groups of chunks compute on one of a few compute streams as
+soon as they have landed, and results return on a third stream (PCIe is full duplex).
 
     pipe = HostPipeline(sa_module, chunk_clouds=148, n_streams=2)
     pipe(host_feats, out_xyz_host, out_points_host)      # all pinned; returns after a full sync
@@ -13,7 +13,7 @@ as it has landed, and results return on a third stream (PCIe is full duplex).
 """
 from __future__ import annotations
 
-from typing import List
+from typing import List, Sequence
 
 import torch
 
@@ -21,42 +21,67 @@ from . import pointnet2_utils as pn2
 
 
 class HostPipeline:
-    """``n_streams`` compute streams; the H2D and D2H copies run on two dedicated streams so that
-    the host-to-device engine streams the whole batch back to back (it is the bottleneck: the
-    kernels of a chunk take less time than its PCIe transfer) while chunks compute as they land."""
+    """H2D copies run back to back on a dedicated stream in chunks of ``chunk_clouds`` into ONE device
+    buffer; compute runs on ``n_streams`` streams over GROUPS of consecutive chunks (``groups``: chunks
+    per group in order, the last but one repeating, the last entry being the size of the final group) as soon as the last chunk of a group has landed;
+    results return on a third stream.  Measured on B200 (1184 clouds of 24k points, scripts/gpu_e2e_sweep.sh):
+    one chunk per group is best (5.9e7 sampled points/s); larger groups start later than they gain in
+    kernel efficiency ((2,3,2,1): 5.5e7, (2,5,1): 4.6e7), so that is the default."""
 
-    def __init__(self, module: torch.nn.Module, chunk_clouds: int = 148, n_streams: int = 2):
+    def __init__(self, module: torch.nn.Module, chunk_clouds: int = 148, n_streams: int = 2,
+                 groups: Sequence[int] = (1,)):
         self.module = module
         self.chunk = int(chunk_clouds)
+        self.groups = tuple(int(g) for g in groups) or (1,)
         self.streams: List[torch.cuda.Stream] = [torch.cuda.Stream() for _ in range(max(1, int(n_streams)))]
         self.copy_in = torch.cuda.Stream()
         self.copy_out = torch.cuda.Stream()
+        self._dev = None
+
+    def _plan(self, B: int):
+        """[(lo, hi)] of the chunks and [(first_chunk, last_chunk)] of the compute groups."""
+        spans = [(lo, min(B, lo + self.chunk)) for lo in range(0, B, self.chunk)]
+        body, tail = self.groups[:-1], self.groups[-1]
+        plan, k, i = [], 0, 0
+        while k < len(spans):
+            remaining = len(spans) - k
+            if remaining <= tail or not body:
+                n = min(remaining, tail)
+            else:                                   # body entries in order, the last one repeating; keep the tail group
+                n = max(1, min(body[min(i, len(body) - 1)], remaining - tail))
+                i += 1
+            plan.append((k, k + n - 1))
+            k += n
+        return spans, plan
 
     @torch.no_grad()
     def __call__(self, host_feats: torch.Tensor, out_xyz_host: torch.Tensor, out_points_host: torch.Tensor) -> None:
         B = host_feats.shape[0]
         main = torch.cuda.current_stream()
+        if self._dev is None or self._dev.shape != host_feats.shape:
+            self._dev = torch.empty(host_feats.shape, dtype=host_feats.dtype, device="cuda")
+        dev = self._dev
         self.copy_in.wait_stream(main)
         self.copy_out.wait_stream(main)
         for s in self.streams:
             s.wait_stream(main)
-        spans = [(lo, min(B, lo + self.chunk)) for lo in range(0, B, self.chunk)]
-        # FPS shape for the clouds resident on the GPU (all compute streams), not for one chunk
-        saved_mode = pn2._fps_mode
-        pn2.set_fps_mode(pn2.fps_mode_for_clouds_in_flight(min(B, self.chunk * len(self.streams)), host_feats.shape[2]))
+        spans, plan = self._plan(B)
         landed = []
         with torch.cuda.stream(self.copy_in):                  # every H2D copy queued up front, back to back
             for lo, hi in spans:
-                d = host_feats[lo:hi].to("cuda", non_blocking=True)
+                dev[lo:hi].copy_(host_feats[lo:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.copy_in)
-                landed.append((d, ev))
-        for k, (lo, hi) in enumerate(spans):
-            d, ev = landed[k]
-            s = self.streams[k % len(self.streams)]
-            s.wait_event(ev)
-            d.record_stream(s)
+                landed.append(ev)
+        saved_mode = pn2._fps_mode
+        for gi, (k0, k1) in enumerate(plan):
+            lo, hi = spans[k0][0], spans[k1][1]
+            s = self.streams[gi % len(self.streams)]
+            s.wait_event(landed[k1])
+            # FPS shape for the clouds resident on the GPU (this group and its neighbour on the other stream)
+            pn2.set_fps_mode(pn2.fps_mode_for_clouds_in_flight(min(B, (hi - lo) * len(self.streams)), host_feats.shape[2]))
             with torch.cuda.stream(s):
+                d = dev[lo:hi]
                 new_xyz, new_points = self.module(d[:, :3].contiguous(), d)
                 done = torch.cuda.Event()
                 done.record(s)
@@ -66,8 +91,8 @@ class HostPipeline:
             with torch.cuda.stream(self.copy_out):
                 out_xyz_host[lo:hi].copy_(new_xyz, non_blocking=True)
                 out_points_host[lo:hi].copy_(new_points, non_blocking=True)
-        landed.clear()
         pn2.set_fps_mode(saved_mode)
         main.wait_stream(self.copy_out)
+        main.wait_stream(self.copy_in)
         for s in self.streams:
             main.wait_stream(s)
