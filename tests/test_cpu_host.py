@@ -189,3 +189,23 @@ def test_bench_reference_arm_prints_contract_line():
                 "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+def test_host_pipeline_plan_covers_every_cloud_once():
+    """Chunk spans and compute groups of HostPipeline (pure host logic): contiguous, complete, ordered."""
+    from toothgroupnetwork_b200.pipeline import HostPipeline
+
+    class Shape:
+        pass
+
+    for chunk, groups, B in [(148, (1,), 1184), (148, (2, 3, 2, 1), 1184), (148, (2, 3, 2, 1), 148 * 11 + 5),
+                             (64, (2, 5, 1), 100), (296, (1,), 10), (148, (2, 2), 1)]:
+        f = Shape()
+        f.chunk, f.groups = chunk, groups
+        spans, plan = HostPipeline._plan(f, B)
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(0 < hi - lo <= chunk for lo, hi in spans)
+        assert plan[0][0] == 0 and plan[-1][1] == len(spans) - 1
+        assert all(a[1] + 1 == b[0] for a, b in zip(plan, plan[1:]))
+        assert all(k0 <= k1 for k0, k1 in plan)

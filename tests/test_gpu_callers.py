@@ -195,3 +195,24 @@ def test_pointnetpp_msg_encoder_decoder_eval_matches_oracle():
     assert torch.equal(x3.cpu(), cx3) and torch.equal(x1.cpu(), cx1)
     for got, want in ((f1, cf1), (f2, cf2), (f3, cf3), (g2, cg2), (g1, cg1), (g0, cg0)):
         assert rel_err(got, want) < 1e-4
+
+
+@pytest.mark.gpu
+def test_host_pipeline_matches_direct_module_call():
+    """pinned host -> chunks -> pinned host gives the same bits as one call on the whole batch
+    (indices are per cloud, the fused MLP is per row: chunking must not change anything)."""
+    from toothgroupnetwork_b200.pipeline import HostPipeline
+    B, N = 10, 6000
+    feats = torch.cat([clouds.arch_features(N, 40 + i) for i in range(B)], 0)
+    sa = pn2.PointNetSetAbstraction(256, 0.1, 32, 9, [32, 32, 64], False).cuda().eval()
+    with torch.no_grad():
+        d = feats.cuda()
+        want_xyz, want_pts = sa(d[:, :3].contiguous(), d)
+    host = feats.pin_memory()
+    ox = torch.empty((B, 3, 256)).pin_memory()
+    op = torch.empty((B, 64, 256)).pin_memory()
+    for groups in ((1,), (2, 1)):
+        ox.zero_(); op.zero_()
+        HostPipeline(sa, chunk_clouds=3, n_streams=2, groups=groups)(host, ox, op)
+        torch.cuda.synchronize()
+        assert torch.equal(ox, want_xyz.cpu()) and torch.equal(op, want_pts.cpu())

@@ -52,11 +52,6 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ pts, int ba
         sx[i] = 0.f; sy[i] = 0.f; sz[i] = 0.f; sn[i] = INFINITY;
     }
 }
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ uint64_t lds_f32x2(uint32_t addr) {      // two adjacent floats as a packed pair
     uint64_t v;
     asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));

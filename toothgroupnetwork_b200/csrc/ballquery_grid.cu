@@ -40,15 +40,6 @@ constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ float sq_norm_unfused(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
-__device__ __forceinline__ float sq_dist_expanded(float ax, float ay, float az, float an, float bx, float by, float bz,
-                                                  float bn) {
-    float dot = __fmul_rn(ax, bx);
-    dot = __fmaf_rn(ay, by, dot);
-    dot = __fmaf_rn(az, bz, dot);
-    float d = __fmul_rn(-2.0f, dot);
-    d = __fadd_rn(d, an);
-    return __fadd_rn(d, bn);
-}
 __device__ __forceinline__ int float_ordered(float f) {
     const int i = __float_as_int(f);
     return i ^ ((i >> 31) & 0x7FFFFFFF);

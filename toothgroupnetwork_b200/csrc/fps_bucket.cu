@@ -41,8 +41,6 @@ namespace {
 
 constexpr int kT = 512;            // sort kernel (latency-bound: more warps per cloud = shorter serial loops)
 constexpr int kNW = kT / 32;
-constexpr int kMT = 512;           // main kernel
-constexpr int kMNW = kMT / 32;
 constexpr int kBP = 64;            // points per bucket: two per lane
 constexpr int kBatch = 2;          // buckets a warp keeps in flight (memory-level parallelism)
 constexpr int kGatherUnroll = 2;   // buckets a sort-kernel warp gathers together

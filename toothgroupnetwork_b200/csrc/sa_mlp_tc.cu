@@ -42,7 +42,6 @@ constexpr int kRows = 128;                            // rows of a tile = thread
 constexpr int kGroups = 4;
 constexpr int kThreads = kRows * kGroups;
 constexpr uint32_t kChunkStrideA = kRows * 16;        // LBO of the A operand: one 16-byte K-chunk of all rows
-constexpr unsigned FULL = 0xffffffffu;
 
 struct TcLayout {
     int kpad[kSaMaxLayers];          // K of layer l, multiple of 8
