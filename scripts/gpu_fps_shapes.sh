@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 CFGS=${CFGS:-1184:-14 1184:-12 2368:-14 2368:-12 2368:-11 4736:-12 4736:-11}
 for cfg in $CFGS; do
   c=${cfg%%:*}; m=${cfg##*:}
-  timeout -k 10 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --clouds $c --fps-mode=$m > gpurun_out/shape_${c}_${m}.log 2>&1
+  timeout -k 10 100 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --clouds $c --fps-mode=$m > gpurun_out/shape_${c}_${m}.log 2>&1
   python - <<PY
 import json
 try:
