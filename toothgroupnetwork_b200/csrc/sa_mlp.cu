@@ -21,7 +21,8 @@ namespace tgn {
 namespace {
 
 constexpr int kRowsMax = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;        // 16 warps: enough warps per scheduler to cover the shared-memory latency of the FMA loop
+constexpr int kWarps = kThreads / 32;
 
 // Build activation rows [xyz_rel | feats] (or [feats | xyz_rel]) for `rows` grouped rows.
 __device__ __forceinline__ void gather_rows_to_smem(const SaParams& p, int b, int s0, int row0_in_group, int rows,
@@ -48,41 +49,50 @@ __device__ __forceinline__ void gather_rows_to_smem(const SaParams& p, int b, in
     (void)row0_in_group;
 }
 
-template <int CPW>   // output columns per warp (8 warps): 4 rows x CPW columns per thread
+// Output columns per warp CPW (kWarps warps): 4 rows x CPW columns per thread.  The accumulators are packed
+// fp32x2 pairs of adjacent output columns (FFMA2: two IEEE fp32 FMAs per issue slot, each rounding like the
+// scalar op -- the scalar FFMA pipe issues every other cycle, so this doubles the FMA rate); the weight pairs
+// come straight out of the 16-byte shared loads.
+template <int CPW>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ act_in, float* __restrict__ act_out, const float* wt,
                                             const float* __restrict__ bias, int cin, int cout, int cout_pad, int cs)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = warp * CPW;
     if (c0 >= cout) return;
-    float acc[4][CPW];
+    uint64_t acc[4][CPW / 2];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < CPW; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < CPW / 2; ++c) acc[r][c] = 0ull;          // (+0.f, +0.f)
+#pragma unroll 2
     for (int ci = 0; ci < cin; ++ci) {
-        float a[4];
+        uint64_t a[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = act_in[(lane + 32 * r) * cs + ci];
+        for (int r = 0; r < 4; ++r) {
+            const float v = act_in[(lane + 32 * r) * cs + ci];
+            a[r] = pack2(v, v);
+        }
 #pragma unroll
         for (int c4 = 0; c4 < CPW / 4; ++c4) {
-            const float4 w = *reinterpret_cast<const float4*>(wt + ci * cout_pad + c0 + 4 * c4);
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wt + ci * cout_pad + c0 + 4 * c4);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                acc[r][4 * c4 + 0] = __fmaf_rn(a[r], w.x, acc[r][4 * c4 + 0]);
-                acc[r][4 * c4 + 1] = __fmaf_rn(a[r], w.y, acc[r][4 * c4 + 1]);
-                acc[r][4 * c4 + 2] = __fmaf_rn(a[r], w.z, acc[r][4 * c4 + 2]);
-                acc[r][4 * c4 + 3] = __fmaf_rn(a[r], w.w, acc[r][4 * c4 + 3]);
+                acc[r][2 * c4 + 0] = fma2(a[r], w.x, acc[r][2 * c4 + 0]);
+                acc[r][2 * c4 + 1] = fma2(a[r], w.y, acc[r][2 * c4 + 1]);
             }
         }
     }
 #pragma unroll
-    for (int c = 0; c < CPW; ++c) {
-        const int co = c0 + c;
-        if (co < cout) {
-            const float bv = __ldg(bias + co);
+    for (int c = 0; c < CPW / 2; ++c) {
+        const int co = c0 + 2 * c;
+        const float b0 = co < cout ? __ldg(bias + co) : 0.f, b1 = co + 1 < cout ? __ldg(bias + co + 1) : 0.f;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) act_out[(lane + 32 * r) * cs + co] = fmaxf(acc[r][c] + bv, 0.f);
+        for (int r = 0; r < 4; ++r) {
+            float v0, v1;
+            unpack2(acc[r][c], v0, v1);
+            if (co < cout) act_out[(lane + 32 * r) * cs + co] = fmaxf(v0 + b0, 0.f);
+            if (co + 1 < cout) act_out[(lane + 32 * r) * cs + co + 1] = fmaxf(v1 + b1, 0.f);
         }
     }
 }
@@ -97,59 +107,75 @@ sa_mlp_fp32_kernel(const SaParams p)
     float* wt = act1 + kRowsMax * cs;                          // [cin][cout_pad] of the current layer
     int* jrow = reinterpret_cast<int*>(wt + p.wt_floats);
 
-    const int b = blockIdx.y;
-    int s0, rows, k0 = 0;
-    if (p.K <= kRowsMax) {
-        s0 = blockIdx.x * p.gpt;
-        rows = min(p.gpt, p.S - s0) * p.K;
-    } else {
-        s0 = blockIdx.x / p.chunks;
-        k0 = (blockIdx.x % p.chunks) * kRowsMax;
-        rows = min(kRowsMax, p.K - k0);
-    }
-    const int* gi = p.gidx + (static_cast<size_t>(b) * p.S + s0) * p.K + k0;
-    for (int r = threadIdx.x; r < kRowsMax; r += kThreads) jrow[r] = r < rows ? __ldg(gi + r) : -1;
-    __syncthreads();
-    gather_rows_to_smem(p, b, s0, k0, rows, jrow, act0, cs);
-    // rows past `rows` are never read back; zero them once so the FMAs stay finite
-    for (int e = threadIdx.x + rows * cs; e < kRowsMax * cs; e += kThreads) act0[e] = 0.f;
-
-    float* cur = act0;
-    float* nxt = act1;
-    for (int l = 0; l < p.L; ++l) {
+    auto stage_weights = [&](int l, float* dst) {             // W[l] (cout x cin, row-major) -> [cin][cout_pad]
         const int cin = p.ch[l], cout = p.ch[l + 1];
         const int cout_pad = (cout + 15) & ~15;
-        __syncthreads();                                        // previous layer done with wt / cur ready
         for (int e = threadIdx.x; e < cin * cout_pad; e += kThreads) {
             const int ci = e / cout_pad, co = e - ci * cout_pad;
-            wt[e] = co < cout ? __ldg(p.W[l] + static_cast<size_t>(co) * cin + ci) : 0.f;
+            dst[e] = co < cout ? __ldg(p.W[l] + static_cast<size_t>(co) * cin + ci) : 0.f;
+        }
+    };
+    if (p.wt_resident)                                        // once per (persistent) CTA
+        for (int l = 0; l < p.L; ++l) stage_weights(l, wt + p.wt_off[l]);
+
+    const long long total_tiles = static_cast<long long>(p.tiles_x) * p.B;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = static_cast<int>(tile / p.tiles_x);
+        const int bx = static_cast<int>(tile - static_cast<long long>(b) * p.tiles_x);
+        int s0, rows, k0 = 0;
+        if (p.K <= kRowsMax) {
+            s0 = bx * p.gpt;
+            rows = min(p.gpt, p.S - s0) * p.K;
+        } else {
+            s0 = bx / p.chunks;
+            k0 = (bx % p.chunks) * kRowsMax;
+            rows = min(kRowsMax, p.K - k0);
+        }
+        __syncthreads();                                        // the previous tile is done with act / jrow
+        const int* gi = p.gidx + (static_cast<size_t>(b) * p.S + s0) * p.K + k0;
+        for (int r = threadIdx.x; r < kRowsMax; r += kThreads) jrow[r] = r < rows ? __ldg(gi + r) : -1;
+        __syncthreads();
+        gather_rows_to_smem(p, b, s0, k0, rows, jrow, act0, cs);
+        // rows past `rows` are never read back; zero them once so the FMAs stay finite
+        for (int e = threadIdx.x + rows * cs; e < kRowsMax * cs; e += kThreads) act0[e] = 0.f;
+
+        float* cur = act0;
+        float* nxt = act1;
+        for (int l = 0; l < p.L; ++l) {
+            const int cin = p.ch[l], cout = p.ch[l + 1];
+            const int cout_pad = (cout + 15) & ~15;
+            __syncthreads();                                    // previous layer done with wt / cur ready
+            const float* wl = wt + (p.wt_resident ? p.wt_off[l] : 0);
+            if (!p.wt_resident) {
+                stage_weights(l, wt);
+                __syncthreads();
+            }
+            const int cpw = (cout + kWarps - 1) / kWarps;
+            if (cpw <= 4) dense_layer<4>(cur, nxt, wl, p.bias[l], cin, cout, cout_pad, cs);
+            else if (cpw <= 8) dense_layer<8>(cur, nxt, wl, p.bias[l], cin, cout, cout_pad, cs);
+            else dense_layer<16>(cur, nxt, wl, p.bias[l], cin, cout, cout_pad, cs);
+            float* t = cur; cur = nxt; nxt = t;
         }
         __syncthreads();
-        const int cpw = (cout + 7) / 8;
-        if (cpw <= 4) dense_layer<4>(cur, nxt, wt, p.bias[l], cin, cout, cout_pad, cs);
-        else if (cpw <= 8) dense_layer<8>(cur, nxt, wt, p.bias[l], cin, cout, cout_pad, cs);
-        else dense_layer<16>(cur, nxt, wt, p.bias[l], cin, cout, cout_pad, cs);
-        float* t = cur; cur = nxt; nxt = t;
-    }
-    __syncthreads();
 
-    // ---- max over the K rows of each group, channel-first store --------------------------------
-    const int cout = p.ch[p.L];
-    float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
-    if (p.K <= kRowsMax) {
-        const int groups = rows / p.K;
-        for (int e = threadIdx.x; e < groups * cout; e += kThreads) {
-            const int g = e / cout, co = e - g * cout;
-            float m = cur[(g * p.K) * cs + co];
-            for (int k = 1; k < p.K; ++k) m = fmaxf(m, cur[(g * p.K + k) * cs + co]);
-            ob[static_cast<size_t>(co) * p.S + s0 + g] = m;
-        }
-    } else {
-        for (int co = threadIdx.x; co < cout; co += kThreads) {
-            float m = cur[co];
-            for (int k = 1; k < rows; ++k) m = fmaxf(m, cur[k * cs + co]);
-            // post-ReLU values are >= 0, so integer order == float order and 0 is the identity
-            atomicMax(reinterpret_cast<int*>(ob + static_cast<size_t>(co) * p.S + s0), __float_as_int(m));
+        // ---- max over the K rows of each group, channel-first store --------------------------------
+        const int cout = p.ch[p.L];
+        float* ob = p.out + (static_cast<size_t>(b) * p.out_c_total + p.out_c_offset) * p.S;
+        if (p.K <= kRowsMax) {
+            const int groups = rows / p.K;
+            for (int e = threadIdx.x; e < groups * cout; e += kThreads) {
+                const int g = e / cout, co = e - g * cout;
+                float m = cur[(g * p.K) * cs + co];
+                for (int k = 1; k < p.K; ++k) m = fmaxf(m, cur[(g * p.K + k) * cs + co]);
+                ob[static_cast<size_t>(co) * p.S + s0 + g] = m;
+            }
+        } else {
+            for (int co = threadIdx.x; co < cout; co += kThreads) {
+                float m = cur[co];
+                for (int k = 1; k < rows; ++k) m = fmaxf(m, cur[k * cs + co]);
+                // post-ReLU values are >= 0, so integer order == float order and 0 is the identity
+                atomicMax(reinterpret_cast<int*>(ob + static_cast<size_t>(co) * p.S + s0), __float_as_int(m));
+            }
         }
     }
 }
@@ -158,12 +184,21 @@ sa_mlp_fp32_kernel(const SaParams p)
 
 int sa_mlp_fp32_launch(SaParams p, cudaStream_t st)
 {
-    int cmax = 0, wmax = 0;
+    int cmax = 0, wmax = 0, wsum = 0;
     for (int l = 0; l <= p.L; ++l) cmax = std::max(cmax, p.ch[l]);
-    for (int l = 0; l < p.L; ++l) wmax = std::max(wmax, p.ch[l] * ((p.ch[l + 1] + 15) & ~15));
+    for (int l = 0; l < p.L; ++l) {
+        const int wl = p.ch[l] * ((p.ch[l + 1] + 15) & ~15);
+        p.wt_off[l] = wsum;
+        wmax = std::max(wmax, wl);
+        wsum += (wl + 3) & ~3;
+    }
     p.cstride = cmax | 1;                       // odd row stride: conflict-free column walks
-    p.wt_floats = (wmax + 3) & ~3;
-    const size_t smem = (2ull * kRowsMax * p.cstride + p.wt_floats) * sizeof(float) + kRowsMax * sizeof(int);
+    // every layer's weights resident in shared memory when they fit next to the two activation buffers
+    // (then a persistent CTA stages them once); else one layer at a time, re-staged per tile
+    const size_t fixed = 2ull * kRowsMax * p.cstride * sizeof(float) + kRowsMax * sizeof(int);
+    p.wt_resident = fixed + static_cast<size_t>(wsum) * sizeof(float) <= 226 * 1024 ? 1 : 0;
+    p.wt_floats = p.wt_resident ? wsum : ((wmax + 3) & ~3);
+    const size_t smem = fixed + static_cast<size_t>(p.wt_floats) * sizeof(float);
     if (smem > 227 * 1024) { set_error("sa_group_mlp_max: %zu bytes of shared memory needed", smem); return TGN_ERR_INVALID; }
     static size_t configured = 0;
     if (smem > configured) {
@@ -171,21 +206,24 @@ int sa_mlp_fp32_launch(SaParams p, cudaStream_t st)
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
         configured = smem;
     }
-    dim3 grid;
     if (p.K <= kRowsMax) {
         p.gpt = kRowsMax / p.K;
         p.chunks = 1;
-        grid = dim3((p.S + p.gpt - 1) / p.gpt, p.B);
+        p.tiles_x = (p.S + p.gpt - 1) / p.gpt;
     } else {
         p.gpt = 1;
         p.chunks = (p.K + kRowsMax - 1) / kRowsMax;
-        grid = dim3(p.S * p.chunks, p.B);
+        p.tiles_x = p.S * p.chunks;
         // partial maxima are merged with atomicMax: clear this branch's slice of out first
         const cudaError_t e = cudaMemset2DAsync(p.out + static_cast<size_t>(p.out_c_offset) * p.S,
                                                 static_cast<size_t>(p.out_c_total) * p.S * sizeof(float), 0,
                                                 static_cast<size_t>(p.ch[p.L]) * p.S * sizeof(float), p.B, st);
         if (e != cudaSuccess) { set_error("cudaMemset2DAsync: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
     }
+    // persistent CTAs (as many per SM as shared memory and the 2048-thread limit allow) over the flattened tile list
+    const long long total_tiles = static_cast<long long>(p.tiles_x) * p.B;
+    const long long per_sm = std::max<long long>(1, std::min<long long>(2048 / kThreads, (227 * 1024) / (smem + 1024)));
+    const dim3 grid(static_cast<unsigned>(std::min<long long>(total_tiles, per_sm * sm_count())));
     sa_mlp_fp32_kernel<<<grid, kThreads, smem, st>>>(p);
     return check_launch("sa_mlp_fp32_kernel");
 }

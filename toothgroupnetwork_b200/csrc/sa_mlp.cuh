@@ -22,6 +22,9 @@ struct SaParams {
     int out_c_total, out_c_offset;
     // filled by the launchers
     int cstride, wt_floats, gpt, chunks;
+    int wt_resident;                 // fp32 engine: 1 = the weights of all layers stay in shared memory (wt_off), 0 = staged per layer
+    int wt_off[kSaMaxLayers];        // float offsets of the layers' [cin][cout_pad] blocks
+    int tiles_x;                     // fp32 engine: tiles per cloud (grid is flattened and persistent)
 };
 
 int sa_mlp_fp32_launch(SaParams p, cudaStream_t st);
