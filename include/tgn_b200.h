@@ -138,7 +138,9 @@ int tgn_transpose_cn(int B, int C, int N, const float *in, float *out, void *str
  *   n_layers in [1,4]; channels[n_layers+1] HOST array, channels[0] = 3 + D; every width <= 128
  *   weights[l] (C_{l+1}, C_l) row-major DEVICE, biases[l] (C_{l+1}) DEVICE; the two pointer arrays are HOST arrays
  *   out: channel-first (B, out_c_total, S); this branch writes channels [out_c_offset, +C_last)
- *   engine: 0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 3xTF32 tensor-core kernel. */
+ *   engine: 0 = auto (2 when the shape fits it, else 3, else 1), 1 = fp32 CUDA-core kernel (exact FMA),
+ *           2 = tcgen05 3xTF32 kernel (widths <= 64, ~2^-21), 3 = tcgen05 kernel for wide layers (first layer
+ *           3xTF32, later layers as three bf16x2-split MMAs, ~1e-5; at least two layers, K in {16,32,64,128}). */
 int tgn_sa_group_mlp_max(int B, int N, int S, int K, int D, const float *xyz, const float *feats, const float *new_xyz,
                          const int *group_idx, int xyz_first, int n_layers, const int *channels,
                          const float *const *weights, const float *const *biases, float *out, int out_c_total,

@@ -29,7 +29,7 @@ with torch.no_grad():
         for path, name in ((pn2.BALL_AUTO, "auto"), (pn2.BALL_TILE, "tile"), (pn2.BALL_GRID, "grid")):
             print(f"  ball r={r} K={K} {name}: {timeit(lambda: pn2._ball_query(r, K, xyz_t, new_xyz_t, False, path)):.2f} ms")
     ms = pn2.PointNetSetAbstraction(1024, 0.05, 64, 9, [128, 128], False).cuda().eval()
-    for eng, name in ((pn2.ENGINE_AUTO, "auto"), (pn2.ENGINE_FP32, "fp32")):
+    for eng, name in ((pn2.ENGINE_AUTO, "auto"), (pn2.ENGINE_FP32, "fp32"), (pn2.ENGINE_TCW, "tcw")):
         pn2.set_sa_engine(eng)
         try:
             print(f"  SSG r=0.05 K=64 9->[128,128] engine {name}: {timeit(lambda: ms(xyz, feats)):.2f} ms (incl. FPS + ball)")

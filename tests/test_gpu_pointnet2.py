@@ -306,6 +306,40 @@ def test_fused_sa_matches_oracle(N, S, r, K, D, widths, engine):
     assert rel_err(npts.cpu().numpy(), want.numpy()) < REL_TOL
 
 
+WIDE_SHAPES = [
+    # (N, S, r, K, D, widths)   the wide tcgen05 engine (tf32 first layer, bf16x2-split later layers)
+    (24000, 1024, 0.05, 64, 6, [128, 128]),          # real pointnet_pp SA1 branch (pointnet_pp.py:13)
+    (24000, 1024, 0.025, 32, 6, [128, 128]),
+    (6000, 500, 0.1, 16, 6, [64, 64, 128]),          # three layers, partial last tile
+    (3000, 200, 0.2, 128, 0, [32, 100]),             # xyz only, K = 128, odd last width
+]
+
+
+@pytest.mark.parametrize("N,S,r,K,D,widths", WIDE_SHAPES)
+def test_wide_tensor_core_engine_matches_oracle(N, S, r, K, D, widths):
+    B = 2
+    feats = torch.cat([clouds.arch_features(N, 30), clouds.arch_features(N, 31)], 0)
+    points = feats if D == 6 else None
+    xyz = feats[:, :3].contiguous()
+    layers = _random_layers([3 + D] + widths, 11)
+    want_xyz, want = oracle.set_abstraction(xyz, points, S, r, K, layers)
+    sa = pn2.PointNetSetAbstraction(S, r, K, 3 + D, widths, False).cuda().eval()
+    fill_module(sa.mlp_convs, sa.mlp_bns, layers)
+    outs = {}
+    for engine in (pn2.ENGINE_TCW, pn2.ENGINE_FP32):
+        pn2.set_sa_engine(engine)
+        try:
+            with torch.no_grad():
+                nx, npts = sa(xyz.cuda(), None if points is None else points.cuda())
+        finally:
+            pn2.set_sa_engine(pn2.ENGINE_AUTO)
+        assert np.array_equal(nx.cpu().numpy(), want_xyz.numpy())
+        outs[engine] = npts.cpu().numpy()
+        assert rel_err(outs[engine], want.numpy()) < REL_TOL, f"engine {engine}"
+    # the bf16x2 split keeps 16 mantissa bits per operand: expect ~1e-5 against the exact-FMA engine
+    assert rel_err(outs[pn2.ENGINE_TCW], outs[pn2.ENGINE_FP32]) < 5e-5
+
+
 def test_fused_engines_agree_and_auto_prefers_tensor_cores():
     feats = clouds.arch_features(6000, 3).cuda()
     sa = pn2.PointNetSetAbstraction(512, 0.1, 32, 9, [32, 32, 64], False).cuda().eval()

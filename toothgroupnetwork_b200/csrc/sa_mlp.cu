@@ -256,9 +256,16 @@ extern "C" int tgn_sa_group_mlp_max(int B, int N, int S, int K, int D, const flo
     for (int l = 0; l < n_layers; ++l) { p.W[l] = weights[l]; p.bias[l] = biases[l]; }
     p.out = out; p.out_c_total = out_c_total; p.out_c_offset = out_c_offset;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // auto: the 3xTF32 tensor-core engine when the shape fits it (widths <= 64), else the wide tensor-core
+    // engine (tf32 first layer, bf16x2-split later layers: ~1e-5 relative, inside the 1e-4 bar), else the
+    // exact-FMA CUDA-core engine (any K, widths <= 128)
     if (engine == 2 || (engine == 0 && sa_mlp_tc_supported(p))) {
         if (!sa_mlp_tc_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
         return sa_mlp_tc_launch(p, st);
+    }
+    if (engine == 3 || (engine == 0 && sa_mlp_tcw_supported(p))) {
+        if (!sa_mlp_tcw_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the wide tcgen05 engine"); return TGN_ERR_INVALID; }
+        return sa_mlp_tcw_launch(p, st);
     }
     return sa_mlp_fp32_launch(p, st);
 }

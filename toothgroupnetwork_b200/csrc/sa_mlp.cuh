@@ -30,5 +30,7 @@ struct SaParams {
 int sa_mlp_fp32_launch(SaParams p, cudaStream_t st);
 bool sa_mlp_tc_supported(const SaParams& p);
 int sa_mlp_tc_launch(SaParams p, cudaStream_t st);
+bool sa_mlp_tcw_supported(const SaParams& p);     // wide hidden layers: tf32 first layer, bf16x2-split later layers
+int sa_mlp_tcw_launch(SaParams p, cudaStream_t st);
 
 }  // namespace tgn

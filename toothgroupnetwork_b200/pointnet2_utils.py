@@ -35,7 +35,7 @@ from . import pointops
 
 SA_FUSED_MAX_WIDTH = 128
 SA_FUSED_MAX_LAYERS = 4
-ENGINE_AUTO, ENGINE_FP32, ENGINE_TC = 0, 1, 2
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TC, ENGINE_TCW = 0, 1, 2, 3     # TCW: wide layers, tf32 first layer + bf16x2-split later layers
 _sa_engine = ENGINE_AUTO
 
 
