@@ -13,7 +13,9 @@
 //     tighter than the TF32 the reference's own convolutions run in by default, inside
 //     the 1e-4 bar (measured ~1e-5 end to end), at half the operand bytes and half the MMA count of 3xTF32;
 //   * biases are added in the epilogue in fp32 (exact), not through an extra MMA.
-// Two tile groups per CTA (operand tile 64 KB each, 80 KB of weights), persistent over tiles.
+// Two tile groups per CTA at 128 channels (operand tile 64 KB each, 80 KB of weights), four when the layers
+// are narrow enough; persistent over tiles.  On narrow shapes the 3xTF32 engine is faster (bench shape
+// 9->[32,32,64]: 3.8 ms against 5.3 ms here) and more accurate, so the dispatcher prefers it when it fits.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -26,15 +28,15 @@ namespace tgn {
 namespace {
 
 constexpr int kRows = 128;
-constexpr int kGroups = 2;
-constexpr int kThreads = kRows * kGroups;
+constexpr int kMaxGroups = 4;          // tile groups per CTA: 4 when the operand tiles are small enough, else 2
 constexpr uint32_t kChunk = kRows * 16;               // bytes of one 16-byte K-chunk of all 128 rows (LBO of a 128-row operand)
 
 struct WLayout {
     int kpad[kSaMaxLayers];          // K of layer l (layer 0: multiple of 8, 16 at most; later: multiple of 16)
     int npad[kSaMaxLayers];          // N of layer l, multiple of 16
     uint32_t w_hi[kSaMaxLayers], w_lo[kSaMaxLayers];   // byte offsets of the weight operands
-    uint32_t act[kGroups];           // per group operand buffer: [hi | lo], lo at act_lo_off
+    uint32_t act[kMaxGroups];        // per group operand buffer: [hi | lo], lo at act_lo_off
+    int groups;
     uint32_t act_lo_off;
     uint32_t misc, total;
     int tiles_per_cloud, gpt;
@@ -156,9 +158,11 @@ __device__ __forceinline__ float max16(const uint32_t (&v)[32]) {
     return m;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kGroups>
+__global__ void __launch_bounds__(kRows * kGroups, 1)
 sa_mlp_tcw_kernel(const SaParams p, const WLayout lay)
 {
+    constexpr int kThreads = kRows * kGroups;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -388,8 +392,9 @@ sa_mlp_tcw_kernel(const SaParams p, const WLayout lay)
     }
 }
 
-bool make_wlayout(const SaParams& p, WLayout& lay)
+bool make_wlayout_groups(const SaParams& p, WLayout& lay, int kGroups)
 {
+    lay.groups = kGroups;
     if (p.L < 2 || p.L > kSaMaxLayers) return false;                       // one layer: the other engines
     if (!(p.K == 16 || p.K == 32 || p.K == 64 || p.K == 128)) return false;
     if (p.ch[0] > 16) return false;                                        // the gathered row is built in 16 registers
@@ -425,6 +430,27 @@ bool make_wlayout(const SaParams& p, WLayout& lay)
     return lay.total <= 224 * 1024;
 }
 
+// four tile groups when they fit (narrow layers), else two
+bool make_wlayout(const SaParams& p, WLayout& lay)
+{
+    return make_wlayout_groups(p, lay, 4) || make_wlayout_groups(p, lay, 2);
+}
+
+template <int kGroups>
+int launch_tcw(const SaParams& p, const WLayout& lay, cudaStream_t st)
+{
+    static uint32_t configured = 0;
+    if (lay.total > configured) {
+        const cudaError_t e = cudaFuncSetAttribute(sa_mlp_tcw_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lay.total));
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
+        configured = lay.total;
+    }
+    const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
+    const int grid = static_cast<int>(std::min<long long>((tiles + kGroups - 1) / kGroups, sm_count()));
+    sa_mlp_tcw_kernel<kGroups><<<grid, kRows * kGroups, lay.total, st>>>(p, lay);
+    return check_launch("sa_mlp_tcw_kernel");
+}
+
 }  // namespace
 
 bool sa_mlp_tcw_supported(const SaParams& p)
@@ -437,16 +463,7 @@ int sa_mlp_tcw_launch(SaParams p, cudaStream_t st)
 {
     WLayout lay{};
     if (!make_wlayout(p, lay)) { set_error("sa_group_mlp_max: shape not supported by the wide tcgen05 engine"); return TGN_ERR_INVALID; }
-    static uint32_t configured = 0;
-    if (lay.total > configured) {
-        const cudaError_t e = cudaFuncSetAttribute(sa_mlp_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lay.total));
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
-        configured = lay.total;
-    }
-    const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
-    const int grid = static_cast<int>(std::min<long long>((tiles + kGroups - 1) / kGroups, sm_count()));
-    sa_mlp_tcw_kernel<<<grid, kThreads, lay.total, st>>>(p, lay);
-    return check_launch("sa_mlp_tcw_kernel");
+    return lay.groups == 4 ? launch_tcw<4>(p, lay, st) : launch_tcw<2>(p, lay, st);
 }
 
 }  // namespace tgn
