@@ -22,10 +22,13 @@
 
 #include "common.cuh"
 #include "sa_mlp.cuh"
+#include "tc_common.cuh"
 #include "tgn_b200.h"
 
 namespace tgn {
 namespace {
+
+using namespace tc;
 
 constexpr int kRows = 128;
 constexpr int kMaxGroups = 4;          // tile groups per CTA: 4 when the operand tiles are small enough, else 2
@@ -43,64 +46,6 @@ struct WLayout {
     uint32_t tpc_magic;
 };
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= static_cast<uint64_t>((128u >> 4) & 0x3FFFu) << 32;      // SBO = 128 B: 8 rows of 16 bytes
-    d |= 1ull << 46;
-    return d;
-}
-__device__ __forceinline__ uint32_t idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(kRows >> 4) << 24);
-}
-__device__ __forceinline__ uint32_t idesc_bf16(int n) {      // D = f32, A = B = bf16, both K-major
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(kRows >> 4) << 24);
-}
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, bool acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(static_cast<uint32_t>(acc)) : "memory");
-}
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, bool acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(static_cast<uint32_t>(acc)) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kRows) : "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(a) & 0xFFFFE000u;
-    lo = __float_as_uint(__fsub_rn(a, __uint_as_float(hi)));
-}
 // (a, b) -> packed bf16 pair, a in the LOW half (the lower K index), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     uint32_t r;
@@ -113,10 +58,6 @@ __device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, 
     const float a1 = __uint_as_float(hi << 16), b1 = __uint_as_float(hi & 0xFFFF0000u);
     lo = pack_bf16(__fsub_rn(a, a1), __fsub_rn(b, b1));
 }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
 // Inner-layer epilogue of one thread (row r): NP accumulator columns -> + bias, ReLU, bf16 hi/lo split,
 // 16-byte stores (8 K-elements each) into the next layer's K-major operand.
 template <int NP>
@@ -292,44 +233,44 @@ sa_mlp_tcw_kernel(const SaParams p, const WLayout lay)
                 const uint64_t step = (2 * kChunk) >> 4;         // two 16-byte K-chunks of a 128-row operand per MMA
                 if (l == 0) {
                     // D[row, n] += X0[row, k] * W0[n, k], 3xTF32, K = 8 per MMA
-                    const uint32_t idesc = idesc_tf32(np);
+                    const uint32_t idesc = make_idesc_tf32(np);
                     const uint32_t lbo_w = static_cast<uint32_t>(np) * 16;
-                    uint64_t d_xh = make_desc(x_hi, kChunk), d_xl = make_desc(a0_lo, kChunk);
-                    uint64_t d_wh = make_desc(sbase + lay.w_hi[0], lbo_w), d_wl = make_desc(sbase + lay.w_lo[0], lbo_w);
+                    uint64_t d_xh = make_smem_desc(x_hi, kChunk), d_xl = make_smem_desc(a0_lo, kChunk);
+                    uint64_t d_wh = make_smem_desc(sbase + lay.w_hi[0], lbo_w), d_wl = make_smem_desc(sbase + lay.w_lo[0], lbo_w);
                     const uint64_t step_w = (2 * lbo_w) >> 4;
                     for (int ks = 0; ks < kp / 8; ++ks) {
                         if (lane == 0) {
-                            mma_tf32(tmem_base, d_xh, d_wh, idesc, ks > 0);
-                            mma_tf32(tmem_base, d_xl, d_wh, idesc, true);
-                            mma_tf32(tmem_base, d_xh, d_wl, idesc, true);
+                            mma_tf32_ss(tmem_base, d_xh, d_wh, idesc, ks > 0);
+                            mma_tf32_ss(tmem_base, d_xl, d_wh, idesc, true);
+                            mma_tf32_ss(tmem_base, d_xh, d_wl, idesc, true);
                         }
                         d_xh += step; d_xl += step; d_wh += step_w; d_wl += step_w;
                     }
                 } else if (!last) {
                     // D[row, n] += X[row, k] * W[n, k], three bf16 terms, K = 16 per MMA
-                    const uint32_t idesc = idesc_bf16(np);
+                    const uint32_t idesc = make_idesc_bf16(np);
                     const uint32_t lbo_w = static_cast<uint32_t>(np) * 16;
-                    uint64_t d_xh = make_desc(x_hi, kChunk), d_xl = make_desc(x_lo, kChunk);
-                    uint64_t d_wh = make_desc(sbase + lay.w_hi[l], lbo_w), d_wl = make_desc(sbase + lay.w_lo[l], lbo_w);
+                    uint64_t d_xh = make_smem_desc(x_hi, kChunk), d_xl = make_smem_desc(x_lo, kChunk);
+                    uint64_t d_wh = make_smem_desc(sbase + lay.w_hi[l], lbo_w), d_wl = make_smem_desc(sbase + lay.w_lo[l], lbo_w);
                     const uint64_t step_w = (2 * lbo_w) >> 4;
                     for (int ks = 0; ks < kp / 16; ++ks) {
                         if (lane == 0) {
-                            mma_bf16(tmem_base, d_xh, d_wh, idesc, ks > 0);
-                            mma_bf16(tmem_base, d_xl, d_wh, idesc, true);
-                            mma_bf16(tmem_base, d_xh, d_wl, idesc, true);
+                            mma_bf16_ss(tmem_base, d_xh, d_wh, idesc, ks > 0);
+                            mma_bf16_ss(tmem_base, d_xl, d_wh, idesc, true);
+                            mma_bf16_ss(tmem_base, d_xh, d_wl, idesc, true);
                         }
                         d_xh += step; d_xl += step; d_wh += step_w; d_wl += step_w;
                     }
                 } else {
                     // D^T[channel, row] += W[channel, k] * X[row, k], three bf16 terms
-                    const uint32_t idesc = idesc_bf16(kRows);
-                    uint64_t d_xh = make_desc(x_hi, kChunk), d_xl = make_desc(x_lo, kChunk);
-                    uint64_t d_wh = make_desc(sbase + lay.w_hi[l], kChunk), d_wl = make_desc(sbase + lay.w_lo[l], kChunk);
+                    const uint32_t idesc = make_idesc_bf16(kRows);
+                    uint64_t d_xh = make_smem_desc(x_hi, kChunk), d_xl = make_smem_desc(x_lo, kChunk);
+                    uint64_t d_wh = make_smem_desc(sbase + lay.w_hi[l], kChunk), d_wl = make_smem_desc(sbase + lay.w_lo[l], kChunk);
                     for (int ks = 0; ks < kp / 16; ++ks) {
                         if (lane == 0) {
-                            mma_bf16(tmem_base, d_wh, d_xh, idesc, ks > 0);
-                            mma_bf16(tmem_base, d_wh, d_xl, idesc, true);
-                            mma_bf16(tmem_base, d_wl, d_xh, idesc, true);
+                            mma_bf16_ss(tmem_base, d_wh, d_xh, idesc, ks > 0);
+                            mma_bf16_ss(tmem_base, d_wh, d_xl, idesc, true);
+                            mma_bf16_ss(tmem_base, d_wl, d_xh, idesc, true);
                         }
                         d_xh += step; d_xl += step; d_wh += step; d_wl += step;
                     }
