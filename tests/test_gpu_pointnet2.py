@@ -190,7 +190,7 @@ def test_feature_propagation_backward_matches_autograd_of_dense_form():
 
 
 # ------------------------------------------------------------------------------------ set abstraction
-@pytest.mark.parametrize("engine", [pn2.ENGINE_FP32, pn2.ENGINE_TC])
+@pytest.mark.parametrize("engine", [pn2.ENGINE_FP32, pn2.ENGINE_TC, pn2.ENGINE_TCW])
 def test_set_abstraction_eval_matches_reference_fixture(golden_dir, engine):
     fix = load(golden_dir, "ref_torch_sa.npz")
     feats = torch.from_numpy(fix["feats"]).cuda()
@@ -218,11 +218,30 @@ def test_set_abstraction_train_mode_matches_reference_fixture(golden_dir):
     assert rel_err(npts.cpu().numpy(), fix["new_points_train"]) < REL_TOL
 
 
-@pytest.mark.parametrize("engine", [pn2.ENGINE_FP32, pn2.ENGINE_TC])
+@pytest.mark.parametrize("engine", [pn2.ENGINE_FP32, pn2.ENGINE_TC, pn2.ENGINE_TCW])
 def test_set_abstraction_msg_eval_matches_reference_fixture(golden_dir, engine):
     fix = load(golden_dir, "ref_torch_msg.npz")
     feats = torch.from_numpy(fix["feats"]).cuda()
     msg = pn2.PointNetSetAbstractionMsg(128, [0.05, 0.1], [16, 32], 6, [[16, 32], [32, 48]]).cuda().eval()
+    for bi in range(2):
+        fill_module(msg.conv_blocks[bi], msg.bn_blocks[bi], layers_from(fix, 2, f"br{bi}_"))
+    pn2.set_sa_engine(engine)
+    try:
+        with torch.no_grad():
+            nx, npts = msg(feats[:, :3].contiguous(), feats)
+    finally:
+        pn2.set_sa_engine(pn2.ENGINE_AUTO)
+    assert np.array_equal(nx.cpu().numpy(), fix["new_xyz_eval"])
+    assert rel_err(npts.cpu().numpy(), fix["new_points_eval"]) < REL_TOL
+
+
+@pytest.mark.parametrize("engine", [pn2.ENGINE_AUTO, pn2.ENGINE_TCW, pn2.ENGINE_FP32])
+def test_real_pointnet_pp_sa1_shape_matches_reference_fixture(golden_dir, engine):
+    """The real pointnet_pp SA1 (pointnet_pp.py:13: two 9->128->128 branches, K = 32 / 64) against a fixture made
+    by the reference's own Python (tests/golden/make_ref_torch_msg128_golden.py).  AUTO takes the wide tcgen05 engine."""
+    fix = load(golden_dir, "ref_torch_msg128.npz")
+    feats = torch.from_numpy(fix["feats"]).cuda()
+    msg = pn2.PointNetSetAbstractionMsg(128, [0.05, 0.1], [32, 64], 6, [[128, 128], [128, 128]]).cuda().eval()
     for bi in range(2):
         fill_module(msg.conv_blocks[bi], msg.bn_blocks[bi], layers_from(fix, 2, f"br{bi}_"))
     pn2.set_sa_engine(engine)

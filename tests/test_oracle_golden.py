@@ -93,6 +93,16 @@ def test_set_abstraction_msg(golden_dir, mode):
     assert _rel(npts.numpy(), fix[f"new_points_{mode}"]) < 1e-4
 
 
+def test_set_abstraction_msg_real_sa1_shape(golden_dir):
+    """Oracle against the reference-Python fixture of the real pointnet_pp SA1 shape (9->128->128 twice)."""
+    fix = _load(golden_dir, "ref_torch_msg128.npz")
+    feats = torch.from_numpy(fix["feats"])
+    branches = [_layers(fix, 2, "br0_"), _layers(fix, 2, "br1_")]
+    nx, npts = oracle.set_abstraction_msg(feats[:, :3].contiguous(), feats, 128, [0.05, 0.1], [32, 64], branches)
+    assert np.array_equal(nx.numpy(), fix["new_xyz_eval"])
+    assert _rel(npts.numpy(), fix["new_points_eval"]) < 1e-4
+
+
 def test_set_abstraction_group_all(golden_dir):
     fix = _load(golden_dir, "ref_torch_groupall.npz")
     feats = torch.from_numpy(fix["feats"])
