@@ -57,6 +57,7 @@ struct TcLayout {
     uint32_t tmem_cols, group_cols;
     int tiles_per_cloud, gpt;
     uint32_t tpc_magic;              // floor(2^32 / tiles_per_cloud): t / tiles_per_cloud by IMAD.HI + one fix-up
+    int a_tmem;                      // 1: the activation operands of the inner layers live in tensor memory
 };
 
 // Inner-layer epilogue of one thread: its accumulator lane (NP columns) -> bias is already in, ReLU,
@@ -82,6 +83,23 @@ __device__ __forceinline__ void mid_epilogue(uint32_t tmem_row, uint32_t a_hi, u
             }
         }
     }
+}
+
+// Same epilogue, but the next layer's A operand goes to TENSOR MEMORY: this thread's lane, hi at column
+// col_hi.., lo at col_lo.. (the tensor core then reads the activations without touching shared memory).
+template <int NP>
+__device__ __forceinline__ void mid_epilogue_tmem(uint32_t tmem_row, uint32_t col_hi, uint32_t col_lo)
+{
+#pragma unroll
+    for (int c0 = 0; c0 < NP; c0 += 16) {
+        uint32_t v[32], hi[16], lo[16];
+        tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_tf32(fmaxf(__uint_as_float(v[i]), 0.f), hi[i], lo[i]);
+        tmem_st16(tmem_row + col_hi + c0, hi);
+        tmem_st16(tmem_row + col_lo + c0, lo);
+    }
+    tmem_wait_st();
 }
 
 // max(0, v[B], ..., v[B+15]) with 3-input FMNMX
@@ -221,7 +239,17 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
         const int rows = groups * p.K;
 
         // ---- layer-0 operand: this thread's grouped row --------------------------------------------
-        if (fast_rows) {
+        if (fast_rows && lay.a_tmem) {
+            // the 16-wide padded row (registers) -> tf32 hi/lo -> this thread's TMEM lane, columns 96.. / 112..
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_tf32(row[i], hi[i], lo[i]);
+            tmem_st16(tmem_row + (kRows - 32), hi);
+            tmem_st16(tmem_row + (kRows - 16), lo);
+            tmem_wait_st();
+            load_row16(tile + tile_step, j_next, row);          // consumed one tile later: latency hidden
+            j_next = load_index(tile + 2 * tile_step);
+        } else if (fast_rows) {
             // the 16-wide padded row was loaded into registers while the previous tile computed
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
@@ -286,13 +314,26 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
                     uint64_t d_whi = make_smem_desc(sbase + lay.w_hi[l], lbo_b, 128);
                     uint64_t d_wlo = make_smem_desc(sbase + lay.w_lo[l], lbo_b, 128);
                     const uint64_t step_w = (2 * lbo_b) >> 4;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        if (lane == 0) {
-                            mma_tf32_ss(tmem_base, d_xhi, d_whi, idesc, ks > 0);
-                            mma_tf32_ss(tmem_base, d_xlo, d_whi, idesc, true);
-                            mma_tf32_ss(tmem_base, d_xhi, d_wlo, idesc, true);
+                    if (lay.a_tmem) {
+                        // A (activations) from tensor memory: hi at column 128 - 2 kp, lo at 128 - kp, 8 columns per K-step
+                        uint32_t t_hi = tmem_base + (kRows - 2 * kp), t_lo = tmem_base + (kRows - kp);
+                        for (int ks = 0; ks < nks; ++ks) {
+                            if (lane == 0) {
+                                mma_tf32_ts(tmem_base, t_hi, d_whi, idesc, ks > 0);
+                                mma_tf32_ts(tmem_base, t_lo, d_whi, idesc, true);
+                                mma_tf32_ts(tmem_base, t_hi, d_wlo, idesc, true);
+                            }
+                            t_hi += 8; t_lo += 8; d_whi += step_w; d_wlo += step_w;
                         }
-                        d_xhi += step_x; d_xlo += step_x; d_whi += step_w; d_wlo += step_w;
+                    } else {
+                        for (int ks = 0; ks < nks; ++ks) {
+                            if (lane == 0) {
+                                mma_tf32_ss(tmem_base, d_xhi, d_whi, idesc, ks > 0);
+                                mma_tf32_ss(tmem_base, d_xlo, d_whi, idesc, true);
+                                mma_tf32_ss(tmem_base, d_xhi, d_wlo, idesc, true);
+                            }
+                            d_xhi += step_x; d_xlo += step_x; d_whi += step_w; d_wlo += step_w;
+                        }
                     }
                     if (lane == 0) {
                         mma_tf32_ss(tmem_base, make_smem_desc(sbase + lay.ones, kChunkStrideA, 128),
@@ -324,7 +365,15 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
             phase ^= 1;
             tc_fence_after();
 
-            if (!last) {
+            if (!last && lay.a_tmem && l + 2 < p.L) {
+                // the next layer is an inner one too: its A operand (K = np) goes to tensor memory
+                const uint32_t ch = kRows - 2 * np, cl = kRows - np;
+                switch (np) {
+                    case 16: mid_epilogue_tmem<16>(tmem_row, ch, cl); break;
+                    case 32: mid_epilogue_tmem<32>(tmem_row, ch, cl); break;
+                    default: mid_epilogue_tmem<48>(tmem_row, ch, cl); break;
+                }
+            } else if (!last) {
                 switch (np) {
                     case 16: mid_epilogue<16>(tmem_row, a_hi, a_lo, r); break;
                     case 32: mid_epilogue<32>(tmem_row, a_hi, a_lo, r); break;
@@ -428,6 +477,14 @@ bool make_layout(const SaParams& p, TcLayout& lay)
     lay.total = off;
     lay.group_cols = kRows;                            // the transposed last layer fills 128 columns per group
     lay.tmem_cols = lay.group_cols * kGroups;          // 512: all of tensor memory (one CTA per SM by design)
+    // activation operands of the inner layers in tensor memory: the accumulator (np columns from 0) and the
+    // hi / lo operands (kp columns each, at the top of the group's 128 columns) must not overlap, also with
+    // the operand the epilogue writes for the next inner layer (np columns each)
+    lay.a_tmem = (p.L >= 2 && lay.kpad[0] == 16) ? 1 : 0;
+    for (int l = 0; l + 1 < p.L && lay.a_tmem; ++l) {
+        if (lay.npad[l] + 2 * lay.kpad[l] > kRows) lay.a_tmem = 0;
+        if (l + 2 < p.L && (lay.npad[l] > 48 || 3 * lay.npad[l] > kRows)) lay.a_tmem = 0;
+    }
     lay.gpt = kRows / p.K;
     lay.tiles_per_cloud = (p.S + lay.gpt - 1) / lay.gpt;
     lay.tpc_magic = static_cast<uint32_t>(std::min<unsigned long long>((1ull << 32) / static_cast<unsigned long long>(lay.tiles_per_cloud), 0xFFFFFFFFull));
