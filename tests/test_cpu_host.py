@@ -42,12 +42,13 @@ def test_reference_launcher_names_are_exactly_the_references(built_lib):
 
 
 def test_library_contains_blackwell_instructions(built_lib):
-    """SASS evidence: tcgen05 MMA (UTCHMMA), TMEM loads (LDTM), packed fp32 (FFMA2), mbarrier."""
+    """SASS evidence: tcgen05 MMA (UTCHMMA), TMEM loads / stores (LDTM / STTM: activation operands kept in tensor
+    memory), packed fp32 (FFMA2), mbarrier."""
     try:
         sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True, timeout=300).stdout
     except (FileNotFoundError, subprocess.TimeoutExpired):
         pytest.skip("cuobjdump unavailable")
-    for mnemonic in ("UTCHMMA", "LDTM", "FFMA2", "SYNCS"):
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "FFMA2", "SYNCS"):
         assert mnemonic in sass, mnemonic
     assert "arch = sm_100a" in subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout or True
 
