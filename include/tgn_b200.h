@@ -19,6 +19,7 @@
 #ifndef TGN_B200_H_
 #define TGN_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -94,6 +95,10 @@ int tgn_grouping_forward(int m, int nsample, int c, const float *input, const in
 int tgn_grouping_backward(int m, int nsample, int c, const float *grad_output, const int *idx, float *grad_input, void *stream);
 int tgn_interpolation_forward(int n, int c, int k, const float *input, const int *idx, const float *weight, float *output, void *stream);
 int tgn_interpolation_backward(int n, int c, int k, const float *grad_output, const int *idx, const float *weight, float *grad_input, void *stream);
+/* output[n,:] += sum_i input[idx[n,i],:] * weight[n,i].  fused = 1: the FMA chain of interpolation_cuda_kernel.cu:5-18
+ * (== tgn_interpolation_forward); fused = 0: product rounded, then added -- the arithmetic of the torch loop in
+ * pointops.interpolation (pointops.py:177-179), which is what the models call. */
+int tgn_weighted_gather(int n, int c, int k, const float *input, const int *idx, const float *weight, float *output, int fused, void *stream);
 int tgn_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2, const int *idx, float *output, void *stream);
 int tgn_subtraction_backward(int n, int nsample, int c, const int *idx, const float *grad_output, float *grad_input1, float *grad_input2, void *stream);
 int tgn_aggregation_forward(int n, int nsample, int c, int w_c, const float *input, const float *position, const float *weight,
@@ -109,18 +114,27 @@ int tgn_aggregation_backward(int n, int nsample, int c, int w_c, const float *in
  * ball is empty.  r2 must be float32(radius**2).  idx64 is a bit set: bit 0 writes int64 (the
  * reference's dtype) instead of int32; by default clouds of >= 8192 points whose balls are sparse
  * are answered by a uniform-grid kernel and the rest by an index-order tile scan (same result);
- * bit 2 (4) forces the tile scan, bit 3 (8) the grid, bit 1 (2) a streaming scan (experiments). */
+ * bit 2 (4) forces the tile scan, bit 3 (8) the grid, bit 1 (2) a streaming scan (experiments).
+ * Bits 4 (16) / 5 (32): |new_xyz|^2 / |xyz|^2 rounded as (x*x + z*z) + y*y instead of (x*x + y*y) + z*z --
+ * torch.sum(p ** 2, -1) on CUDA takes the first form for a contiguous (..., 3) operand and the second for a strided
+ * view (and always on the CPU); the Python layer sets the bits from the layout the reference's call would see. */
 int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float *xyz, const float *new_xyz,
                    void *group_idx, int idx64, void *stream);
 
 /* 3 nearest coarse points by the same expanded distance (pointnet2_utils.py:333-335):
  * xyz1 (B,N,3) fine, xyz2 (B,S,3) coarse, S >= 3 -> dist (B,N,3) ascending, idx (B,N,3) int32. */
 int tgn_three_nn(int B, int N, int S, const float *xyz1, const float *xyz2, float *dist, int *idx, void *stream);
+/* Same with `order`: bit 0 / bit 1 = |xyz1|^2 / |xyz2|^2 in the contiguous-reduce rounding (see tgn_ball_query). */
+int tgn_three_nn_ex(int B, int N, int S, const float *xyz1, const float *xyz2, float *dist, int *idx, int order, void *stream);
 
 /* Weighted 3-point interpolation (pointnet2_utils.py:337-340): weights 1/(dist+1e-8) normalised,
  * points2 (B,S,C) point-major -> out (B,N,C). */
 int tgn_three_interpolate(int B, int N, int S, int C, const float *points2, const float *dist, const int *idx,
                           float *out, void *stream);
+/* norm_alt != 0: the normaliser is summed as (r0 + r2) + r1, torch's CUDA reduce order for the contiguous (B,N,3)
+ * reciprocal tensor; 0: (r0 + r1) + r2, the CPU order. */
+int tgn_three_interpolate_ex(int B, int N, int S, int C, const float *points2, const float *dist, const int *idx,
+                             float *out, int norm_alt, void *stream);
 
 /* Batched row gather: pointnet2_utils.index_points (pointnet2_utils.py:44-61).
  * points (B,N,C), idx (B,M) int32 -> out (B,M,C). */
@@ -145,6 +159,73 @@ int tgn_sa_group_mlp_max(int B, int N, int S, int K, int D, const float *xyz, co
                          const int *group_idx, int xyz_first, int n_layers, const int *channels,
                          const float *const *weights, const float *const *biases, float *out, int out_c_total,
                          int out_c_offset, int engine, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * 1x1-convolution chains with BATCH-STATISTICS BatchNorm (any width), one launch per layer
+ * (PointNetSetAbstraction(Msg).forward pointnet2_utils.py:232-237 / :289-294 and
+ * PointNetFeaturePropagation.forward :346-352 with BatchNorm in training mode -- which is how every
+ * reference call site, inference included, runs them -- and in eval mode for widths the single-kernel
+ * engines above do not take).  Layer l computes the RAW pre-activation, channel-major:
+ *      y[c, r] = sum_k W[c, k] * act(x)[r, k] + bias[c],   r in [0, rows)
+ * where act() is the previous layer's BatchNorm + ReLU applied while the operand is built
+ * (in_affine: 0 none, 1 from the fp64 batch sums `in_stats` = {sum[cin], sumsq[cin]} over `rows` rows,
+ * 2 from running statistics).  tcgen05, operands split into three bf16 parts (six MMAs per K step, fp32-grade:
+ * batch-statistics BatchNorm amplifies rounding differences) or two (`precision` = 2: three MMAs, ~1e-5).
+ * mode 0: the operand row r = (b, n), b = r / rows_per_batch, is read from up to two strided segments,
+ *         x[k] = seg_ptr[i][b*seg_batch_stride[i] + n*seg_row_stride[i] + k'*seg_chan_stride[i]] (strides in floats);
+ * mode 1: neighbourhood gather, r = ((b*S + s)*K + j): [feats[b, gidx[r], :] | xyz[b, gidx[r]] - new_xyz[b, s]]
+ *         (xyz_first = 0, MSG order :285) or [xyz - centre | feats] (xyz_first = 1, SSG order :169); cin = D + 3.
+ * Outputs, each optional: y (cout, rows); stats (2*cout doubles, ACCUMULATED: caller zeroes) = per-channel
+ * sum / sum of squares of y; ymax / ymin (cout, rows/group) = extrema over groups of `group` consecutive rows
+ * (the max over the K neighbours must wait for the BatchNorm scale's sign, so both are kept); with
+ * extrema_atomic != 0 they are merged with atomics into buffers the caller pre-filled with -inf / +inf
+ * (required when 128 % group != 0).  w_packed: tgn_pw_pack_weights of the (cout, cin) weight.
+ * in_update_running != 0 with in_affine == 1 applies torch's momentum update to in_running_mean / _var once. */
+typedef struct {
+    int rows, rows_per_batch, cin, cout;
+    int mode;
+    const float *seg_ptr[2];
+    int seg_channels[2];
+    long long seg_batch_stride[2], seg_row_stride[2], seg_chan_stride[2];
+    const float *xyz, *feats, *new_xyz;
+    const int *gidx;
+    int N, S, K, D, xyz_first;
+    int in_affine, in_update_running;
+    const double *in_stats;
+    const float *in_gamma, *in_beta;
+    float *in_running_mean, *in_running_var;
+    float in_eps, in_momentum;
+    const void *w_packed;
+    const float *bias;
+    float *y;
+    double *stats;
+    float *ymax, *ymin;
+    int group, extrema_atomic;
+    int precision;          /* 0 / 3: three bf16 parts per operand, six MMAs per K step (fp32-grade); 2: two parts, three MMAs (~1e-5) */
+} tgn_pw_layer_t;
+
+/* Final BatchNorm (+ ReLU) of a chain into a channel-first tensor:
+ *   out[b, out_c_offset + c, n] = relu?(scale_c * v + shift_c),  v = src[c, b*rows_per_batch + n]
+ * or, when ymin != NULL, v = (scale_c >= 0 ? src : ymin)[c, ...] (src = the max).  `affine` as in_affine above
+ * (0 = identity), statistics over stat_rows rows. */
+typedef struct {
+    int rows, rows_per_batch, channels, out_channels, out_c_offset, relu;
+    const float *src, *ymin;
+    float *out;
+    int affine, update_running;
+    const double *stats;
+    long long stat_rows;
+    const float *gamma, *beta;
+    float *running_mean, *running_var;
+    float eps, momentum;
+} tgn_pw_apply_t;
+
+size_t tgn_pw_packed_bytes(int cout, int cin);
+int tgn_pw_struct_size(int which);         /* sizeof(tgn_pw_layer_t) (0) / sizeof(tgn_pw_apply_t) (1): binding self-check */
+int tgn_pw_pack_weights(int cout, int cin, const float *w, void *packed, void *stream);
+int tgn_pw_layer_forward(const tgn_pw_layer_t *layer, void *stream);
+int tgn_pw_apply(const tgn_pw_apply_t *p, void *stream);
+int tgn_pw_fill(float *ptr, long long n, float value, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""Operator-level timings on one B200: this library beside the REFERENCE's own GPU path
+(verbatim ``pointops`` kernels from ``oracle/_ref`` + the reference's torch ``pointnet2_utils.py``),
+CUDA events on the launching stream, warm-up, median of ``reps``  (C1(a)/C2 "GPU
+reference").
+
+    python scripts/op_bench.py [--out gpurun_out/op_bench.json] [--sections fps,knn,ball,sa,fp]
+
+Also importable: ``bench.py`` calls ``fps_latency_table`` / ``ref_gpu_step`` for its ``latency_ms`` and
+``ref_gpu`` entries.  Test infrastructure side: the reference legs import ``oracle/``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+
+def time_ms(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def arch_batch(B, N, distinct=8):
+    from toothgroupnetwork_b200 import clouds
+    base = [clouds.arch_features(N, s)[0] for s in range(min(B, distinct))]
+    return torch.stack([base[j % len(base)] for j in range(B)]).contiguous().cuda()      # (B,6,N)
+
+
+def ref_available():
+    from oracle import ref_cuda
+    return ref_cuda.available()
+
+
+# ------------------------------------------------------------------------------------------ FPS
+def fps_latency_table(batches=(1, 16, 148, 1184), npoints=(1024, 4096), N=24000, with_ref=True, ref_max_batch=148):
+    """ms per call of FPS N->M over a batch of B clouds: ours (auto shape) and the verbatim reference kernel."""
+    from toothgroupnetwork_b200 import pointops
+    rows = []
+    for B in batches:
+        feats = arch_batch(B, N)
+        xyz = feats[:, :3].permute(0, 2, 1).contiguous().view(-1, 3)
+        off = (torch.arange(1, B + 1, dtype=torch.int32) * N).cuda()
+        for M in npoints:
+            noff = (torch.arange(1, B + 1, dtype=torch.int32) * M).cuda()
+            ours = time_ms(lambda: pointops.fps_packed(xyz, off, noff, N, B * M))
+            row = {"clouds": B, "n": N, "m": M, "ours_ms": ours, "ours_us_per_iteration": ours * 1e3 / (M - 1)}
+            if with_ref and ref_available() and B <= ref_max_batch:
+                from oracle import ref_cuda
+                ref = time_ms(lambda: ref_cuda.furthestsampling(xyz, off, noff, N, B * M), warm=1, reps=3)
+                row.update({"ref_kernel_ms": ref, "speedup": ref / ours})
+            rows.append(row)
+        del feats, xyz
+    return rows
+
+
+# ------------------------------------------------------------------------------------------ kNN
+KNN_MIX = [  # (label, n_src, m_query, k)   tgnet_fps net 1 launch mix (blocks.py:34-35,69-71, heads.py:44-51)
+    ("enc1 self 24k x 24k k=36", 24000, 24000, 36),
+    ("down 6000 <- 24000 k=24", 24000, 6000, 24),
+    ("enc2 self 6000 k=24", 6000, 6000, 24),
+    ("enc3 self 1500 k=24", 1500, 1500, 24),
+    ("up 24000 <- 6000 k=3", 6000, 24000, 3),
+    ("head 24000 <- 6000 k=1", 6000, 24000, 1),
+    ("head 24000 <- 93 k=1", 93, 24000, 1),
+]
+
+
+def knn_table(with_ref=True):
+    from toothgroupnetwork_b200 import clouds, pointops
+    xyz_full = clouds.dental_arch(24000, 0)[0].cuda()
+    rows = []
+    for label, n, m, k in KNN_MIX:
+        src = xyz_full[torch.linspace(0, 23999, n).long()].contiguous()
+        qry = xyz_full[torch.linspace(0, 23999, m).long()].contiguous()
+        o = torch.tensor([n], dtype=torch.int32).cuda()
+        no = torch.tensor([m], dtype=torch.int32).cuda()
+        ours = time_ms(lambda: pointops.knn_packed(k, src, qry, o, no))
+        row = {"case": label, "n": n, "m": m, "k": k, "ours_ms": ours, "pair_evals": n * m,
+               "ours_gflops_bruteforce_equiv": 8.0 * n * m / ours / 1e6}
+        if with_ref and ref_available():
+            from oracle import ref_cuda
+            ref = time_ms(lambda: ref_cuda.knnquery(k, src, qry, o, no), warm=1, reps=3)
+            a = pointops.knn_packed(k, src, qry, o, no)
+            b = ref_cuda.knnquery(k, src, qry, o, no)
+            row.update({"ref_kernel_ms": ref, "speedup": ref / ours,
+                        "bitwise_idx": bool(torch.equal(a[0], b[0])), "bitwise_d2": bool(torch.equal(a[1], b[1]))})
+        rows.append(row)
+    return rows
+
+
+# ------------------------------------------------------------------------------------------ reference torch path
+_ref_world = None
+
+
+def ref_world():
+    global _ref_world
+    if _ref_world is None:
+        from oracle import ref_models
+        _ref_world = ref_models.World("reference")
+    return _ref_world
+
+
+def ball_table(with_ref=True):
+    from toothgroupnetwork_b200 import pointnet2_utils as pn2
+    rows = []
+    for B in (1, 16):
+        feats = arch_batch(B, 24000)
+        xyz_t = feats[:, :3].permute(0, 2, 1).contiguous()
+        new_xyz = pn2._take_rows(xyz_t.view(-1, 3), pn2._fps_batched(xyz_t, 1024)).view(B, 1024, 3)
+        for r, K in ((0.025, 32), (0.05, 64), (0.1, 32), (0.2, 64)):
+            ours = time_ms(lambda: pn2._ball_query(r, K, xyz_t, new_xyz, True))
+            row = {"clouds": B, "radius": r, "K": K, "ours_ms": ours}
+            if with_ref:
+                w = ref_world()
+                with w:
+                    refpn = w.mod("external_libs.pointnet2_utils.pointnet2_utils")
+                    ref = time_ms(lambda: refpn.query_ball_point(r, K, xyz_t, new_xyz), warm=1, reps=3)
+                    same = bool(torch.equal(refpn.query_ball_point(r, K, xyz_t, new_xyz), pn2._ball_query(r, K, xyz_t, new_xyz, True)))
+                row.update({"ref_torch_ms": ref, "speedup": ref / ours, "bitwise": same})
+            rows.append(row)
+    return rows
+
+
+def _copy_sa(src, dst):
+    dst.load_state_dict(src.state_dict())
+    return dst
+
+
+def ref_gpu_step(B=16, train_bn=False, reps=5):
+    """The BASELINE C2(i) step, ``PointNetSetAbstraction(1024, 0.1, 32, 9, [32,32,64])`` forward on B 24k clouds,
+    through the REFERENCE's own GPU path: verbatim FPS kernel + torch query_ball_point / index_points /
+    Conv2d+BN+ReLU / max (``pointnet2_utils.py:213-239``), IEEE fp32 convolutions.  Returns ms and sampled points/s."""
+    from toothgroupnetwork_b200 import pointnet2_utils as pn2
+    feats = arch_batch(B, 24000)
+    xyz = feats[:, :3].contiguous()
+    torch.manual_seed(0)
+    ours = pn2.PointNetSetAbstraction(1024, 0.1, 32, 9, [32, 32, 64], False).cuda().train(train_bn)
+    w = ref_world()
+    with w, torch.no_grad():
+        refpn = w.mod("external_libs.pointnet2_utils.pointnet2_utils")
+        ref = _copy_sa(ours, refpn.PointNetSetAbstraction(1024, 0.1, 32, 9, [32, 32, 64], False).cuda()).train(train_bn)
+        saved = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            ref_ms = time_ms(lambda: ref(xyz, feats), warm=1, reps=reps)
+            want = ref(xyz, feats)
+        finally:
+            torch.backends.cudnn.allow_tf32 = saved
+    with torch.no_grad():
+        ours_ms = time_ms(lambda: ours(xyz, feats), warm=2, reps=reps)
+        got = ours(xyz, feats)
+    rel = float(((got[1] - want[1]).abs() / want[1].abs().clamp(min=1e-3 * float(want[1].abs().max()))).max())
+    return {"clouds": B, "bn": "train" if train_bn else "eval", "ref_gpu_ms": ref_ms, "ours_ms": ours_ms,
+            "ref_gpu_sampled_points_per_s": B * 1024 / ref_ms * 1e3, "ours_sampled_points_per_s": B * 1024 / ours_ms * 1e3,
+            "speedup": ref_ms / ours_ms, "new_xyz_bitwise": bool(torch.equal(got[0], want[0])), "max_rel_elementwise": rel}
+
+
+def fp_table(with_ref=True):
+    """PointNetFeaturePropagation fp1 of tsg_centroid_module (24000 <- 1024, 134 -> 64 -> 32), train and eval BN."""
+    from toothgroupnetwork_b200 import pointnet2_utils as pn2
+    rows = []
+    feats = arch_batch(1, 24000)
+    xyz1 = feats[:, :3].contiguous()
+    xyz_t = xyz1.permute(0, 2, 1).contiguous()
+    sel = pn2.farthest_point_sample(xyz_t, 1024)
+    xyz2 = pn2.index_points(xyz_t, sel).permute(0, 2, 1).contiguous()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    p2 = torch.randn(1, 128, 1024, device="cuda", generator=g)
+    for train_bn in (True, False):
+        torch.manual_seed(0)
+        ours = pn2.PointNetFeaturePropagation(134, [64, 32]).cuda().train(train_bn)
+        with torch.no_grad():
+            ours_ms = time_ms(lambda: ours(xyz1, xyz2, feats, p2))
+            got = ours(xyz1, xyz2, feats, p2)
+        row = {"bn": "train" if train_bn else "eval", "ours_ms": ours_ms}
+        if with_ref:
+            w = ref_world()
+            with w, torch.no_grad():
+                refpn = w.mod("external_libs.pointnet2_utils.pointnet2_utils")
+                ref = _copy_sa(ours, refpn.PointNetFeaturePropagation(134, [64, 32]).cuda()).train(train_bn)
+                saved = torch.backends.cudnn.allow_tf32
+                torch.backends.cudnn.allow_tf32 = False
+                try:
+                    ref_ms = time_ms(lambda: ref(xyz1, xyz2, feats, p2), warm=1, reps=3)
+                    want = ref(xyz1, xyz2, feats, p2)
+                finally:
+                    torch.backends.cudnn.allow_tf32 = saved
+            rel = float(((got - want).abs() / want.abs().clamp(min=1e-3 * float(want.abs().max()))).max())
+            row.update({"ref_torch_ms": ref_ms, "speedup": ref_ms / ours_ms, "max_rel_elementwise": rel})
+        rows.append(row)
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "op_bench.json"))
+    ap.add_argument("--sections", default="fps,knn,ball,sa,fp")
+    ap.add_argument("--no-ref", action="store_true")
+    args = ap.parse_args()
+    assert torch.cuda.is_available()
+    with_ref = not args.no_ref
+    rep = {"device": torch.cuda.get_device_name(0), "timing": "CUDA events, median, warm-up 1-2"}
+    sec = args.sections.split(",")
+    if "fps" in sec:
+        rep["fps_latency"] = fps_latency_table(with_ref=with_ref)
+    if "knn" in sec:
+        rep["knn"] = knn_table(with_ref=with_ref)
+    if "ball" in sec:
+        rep["ball_query"] = ball_table(with_ref=with_ref)
+    if "sa" in sec:
+        rep["sa1_c2i_step"] = [ref_gpu_step(B, bn) for B in (1, 16) for bn in (False, True)]
+    if "fp" in sec:
+        rep["feature_propagation_fp1"] = fp_table(with_ref=with_ref)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+
+
+if __name__ == "__main__":
+    main()

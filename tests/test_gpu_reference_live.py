@@ -1,0 +1,239 @@
+"""GPU parity against the REFERENCE ITSELF running on the same B200: the reference's unmodified
+``pointnet2_utils.py`` / ``pointops.py`` / ``models/modules/*.py`` (staged as ``oracle/_ref/reference_py.tgz`` by
+``__graft_entry__.build()``, or read from /root/reference) on the verbatim ``pointops`` kernels of ``oracle/_ref``.
+Skipped when that snapshot is absent.  What the CPU fixtures cannot pin -- the reference's CUDA arithmetic
+(cuBLAS K=3 products, the layout-dependent rounding of torch.sum(p ** 2, -1), cuDNN convolutions with batch-statistics
+BatchNorm) -- is pinned here, with the call patterns the reference's modules actually use."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_cuda, ref_models
+from toothgroupnetwork_b200 import clouds
+from toothgroupnetwork_b200 import pointnet2_utils as pn2
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (ref_models.available() and ref_cuda.available()), reason="reference snapshot not staged")]
+REL_TOL = 1e-4
+FLOOR = 0.05      # element-wise |a-b| / max(|b|, FLOOR * max|b|)
+
+_world = {}
+
+
+def world(ops):
+    if ops not in _world:
+        _world[ops] = ref_models.World(ops)
+    return _world[ops]
+
+
+def refpn():
+    return world("reference").mod("external_libs.pointnet2_utils.pointnet2_utils")
+
+
+def elementwise(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    scale = float(b.abs().max()) + 1e-30
+    return float(((a - b).abs() / b.abs().clamp(min=FLOOR * scale)).max())
+
+
+@pytest.fixture(autouse=True)
+def _fp32_library_convs():
+    saved = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pn2.set_reference_device("cuda")
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+
+
+def arch(B, N):
+    return torch.stack([clouds.arch_features(N, s)[0] for s in range(B)]).cuda()      # (B,6,N)
+
+
+# ------------------------------------------------------------------------------------ ball query / 3-NN: indices bit-exact
+@pytest.mark.parametrize("B", [1, 16])
+@pytest.mark.parametrize("r,K", [(0.025, 32), (0.05, 64), (0.1, 32), (0.2, 64)])
+@pytest.mark.parametrize("pattern", ["module", "contiguous"])
+def test_ball_query_bit_exact_vs_reference_on_gpu(B, r, K, pattern):
+    """``module``: the layouts PointNetSetAbstraction(Msg).forward produces (xyz = permuted view of the (B,3,N) slice of
+    the feature tensor, new_xyz = contiguous index_points output); ``contiguous``: both operands contiguous."""
+    feats = arch(B, 24000)
+    xyz = feats[:, :3, :].permute(0, 2, 1)                                  # view, strides (6N, 1, N)
+    with world("reference"):
+        fps = refpn().farthest_point_sample(xyz, 1024)
+        new_xyz = refpn().index_points(xyz, fps)
+        if pattern == "contiguous":
+            xyz = xyz.contiguous()
+        want = refpn().query_ball_point(r, K, xyz, new_xyz)
+    got = pn2.query_ball_point(r, K, xyz, new_xyz)
+    bad = int((got != want).any(-1).sum())
+    assert bad == 0, f"{bad} of {B * 1024} queries differ"
+
+
+@pytest.mark.parametrize("pattern", ["views", "contiguous", "mixed"])
+def test_three_nn_bit_exact_vs_reference_on_gpu(pattern):
+    feats = arch(2, 24000)
+    x1 = feats[:, :3, :].permute(0, 2, 1)
+    with world("reference"):
+        x2 = refpn().index_points(x1, refpn().farthest_point_sample(x1, 1024))        # contiguous (B,1024,3)
+        if pattern == "contiguous":
+            x1 = x1.contiguous()
+        elif pattern == "views":
+            x2 = x2.permute(0, 2, 1).contiguous().permute(0, 2, 1)                    # strided view
+        d = refpn().square_distance(x1, x2)
+        wd, wi = d.sort(dim=-1)
+        wd, wi = wd[:, :, :3], wi[:, :, :3]
+    gd, gi = pn2.three_nn(x1, x2)
+    assert torch.equal(gd, wd)
+    assert torch.equal(gi.long(), wi) or float((torch.gather(d, 2, gi.long()) - wd).abs().max()) == 0.0   # equal distances may swap
+
+
+def test_three_interpolate_bit_exact_vs_reference_lines_on_gpu():
+    """pointnet2_utils.py:333-340 evaluated by torch on the GPU (sort, reciprocal, normalise, weighted sum) against the
+    3-NN + interpolation kernels: identical bits, including the normaliser's CUDA reduce order."""
+    feats = arch(2, 24000)
+    x1 = feats[:, :3, :].permute(0, 2, 1)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    with world("reference"):
+        x2 = refpn().index_points(x1, refpn().farthest_point_sample(x1, 1024))
+        p2 = torch.randn(2, 1024, 64, device="cuda", generator=g)
+        dists = refpn().square_distance(x1, x2)
+        dists, idx = dists.sort(dim=-1)
+        dists, idx = dists[:, :, :3], idx[:, :, :3]
+        dist_recip = 1.0 / (dists + 1e-8)
+        norm = torch.sum(dist_recip, dim=2, keepdim=True)
+        weight = dist_recip / norm
+        want = torch.sum(refpn().index_points(p2, idx) * weight.view(2, 24000, 3, 1), dim=2)
+    gd, gi = pn2.three_nn(x1, x2)
+    got = pn2.three_interpolate(p2, gd, gi)
+    assert torch.equal(gd, dists)
+    bad = int((got != want).sum())
+    assert bad == 0, f"{bad} of {got.numel()} interpolated values differ"
+
+
+# ------------------------------------------------------------------------------------ modules with batch-statistics BatchNorm
+def _copy(src, dst):
+    dst.load_state_dict(src.state_dict())
+    return dst
+
+
+@pytest.mark.parametrize("train_bn", [True, False])
+@pytest.mark.parametrize("B", [1, 3])
+def test_set_abstraction_ssg_vs_reference_module(train_bn, B):
+    feats = arch(B, 8192)
+    xyz = feats[:, :3, :]
+    torch.manual_seed(0)
+    ours = pn2.PointNetSetAbstraction(512, 0.1, 32, 9, [32, 32, 64], False).cuda().train(train_bn)
+    with world("reference"), torch.no_grad():
+        ref = _copy(ours, refpn().PointNetSetAbstraction(512, 0.1, 32, 9, [32, 32, 64], False).cuda()).train(train_bn)
+        want_xyz, want = ref(xyz, feats)
+    before = pn2.L.launch_count()
+    with torch.no_grad():
+        got_xyz, got = ours(xyz, feats)
+    assert pn2.L.launch_count() > before
+    assert torch.equal(got_xyz, want_xyz)
+    assert elementwise(got, want) < REL_TOL
+    if train_bn:      # torch's side effects of a training-mode BatchNorm
+        for a, b in zip(ours.mlp_bns, ref.mlp_bns):
+            assert elementwise(a.running_mean, b.running_mean) < 1e-4 and elementwise(a.running_var, b.running_var) < 1e-4
+            assert int(a.num_batches_tracked) == int(b.num_batches_tracked)
+
+
+@pytest.mark.parametrize("train_bn", [True, False])
+@pytest.mark.parametrize("cfg", [
+    (1024, [0.025, 0.05], [32, 64], 6, [[128, 128], [128, 128]]),           # pointnet_pp.py:13 (scale 4)
+    (1024, [0.025, 0.05], [32, 64], 6, [[32, 32], [32, 32]]),               # tsg_centroid_module.py:10
+    (256, [0.1, 0.2], [32, 64], 6, [[196, 256], [196, 256]]),               # widths of tsg sa3 on raw features
+])
+def test_set_abstraction_msg_vs_reference_module(train_bn, cfg):
+    feats = arch(1, 24000)
+    xyz = feats[:, :3, :]
+    torch.manual_seed(0)
+    ours = pn2.PointNetSetAbstractionMsg(*cfg).cuda().train(train_bn)
+    with world("reference"), torch.no_grad():
+        ref = _copy(ours, refpn().PointNetSetAbstractionMsg(*cfg).cuda()).train(train_bn)
+        want_xyz, want = ref(xyz, feats)
+    with torch.no_grad():
+        got_xyz, got = ours(xyz, feats)
+    assert torch.equal(got_xyz, want_xyz)
+    assert got_xyz.stride() == want_xyz.stride()           # same view layout as the reference hands on
+    assert elementwise(got, want) < REL_TOL
+
+
+@pytest.mark.parametrize("train_bn", [True, False])
+def test_group_all_wide_vs_reference_module(train_bn):
+    """tsg_seg_module.py:26 flatten_sa: PointNetSetAbstraction(None, None, None, 512+3, [256, 512], True) on 256 points."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xyz = torch.rand(2, 3, 256, device="cuda", generator=g)
+    pts = torch.randn(2, 512, 256, device="cuda", generator=g)
+    torch.manual_seed(0)
+    ours = pn2.PointNetSetAbstraction(None, None, None, 515, [256, 512], True).cuda().train(train_bn)
+    with world("reference"), torch.no_grad():
+        ref = _copy(ours, refpn().PointNetSetAbstraction(None, None, None, 515, [256, 512], True).cuda()).train(train_bn)
+        _, want = ref(xyz, pts)
+    with torch.no_grad():
+        _, got = ours(xyz, pts)
+    assert elementwise(got, want) < REL_TOL
+
+
+@pytest.mark.parametrize("train_bn", [True, False])
+@pytest.mark.parametrize("shape", [(24000, 1024, 6, 128, [64, 32]), (512, 256, 512, 1024, [1024, 1024]), (1024, 1, 64, 128, [64])])
+def test_feature_propagation_vs_reference_module(train_bn, shape):
+    N, S, D1, D2, mlp = shape
+    B = 2
+    feats = arch(B, N)
+    xyz1 = feats[:, :3, :]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    with world("reference"):
+        x1v = xyz1.permute(0, 2, 1)
+        if S >= 3:
+            new = refpn().index_points(x1v, refpn().farthest_point_sample(x1v, S))
+        else:
+            new = x1v[:, :1, :].contiguous()
+        xyz2 = new.permute(0, 2, 1)                                             # the view a set-abstraction level returns
+    p1 = torch.randn(B, D1, N, device="cuda", generator=g)
+    p2 = torch.randn(B, D2, S, device="cuda", generator=g)
+    torch.manual_seed(0)
+    ours = pn2.PointNetFeaturePropagation(D1 + D2, mlp).cuda().train(train_bn)
+    with world("reference"), torch.no_grad():
+        ref = _copy(ours, refpn().PointNetFeaturePropagation(D1 + D2, mlp).cuda()).train(train_bn)
+        want = ref(xyz1, xyz2, p1, p2)
+    with torch.no_grad():
+        got = ours(xyz1, xyz2, p1, p2)
+    assert elementwise(got, want) < REL_TOL
+
+
+# ------------------------------------------------------------------------------------ whole models (C2-model, C3, C4)
+def _model_parity():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import model_parity
+    return model_parity
+
+
+def test_pointnet_pp_model_eval_bn_logits_vs_reference():
+    mp = _model_parity()
+    feats, _ = mp.make_inputs(24000)
+    res = mp.case_pp([world("reference"), world("b200")], feats, False, mp.Timer())
+    assert res["indices_identical"]
+    assert res["verdict"]["pass"], res["verdict"]
+
+
+def test_pointnet_pp_model_train_bn_logits_vs_reference():
+    mp = _model_parity()
+    feats, _ = mp.make_inputs(24000)
+    res = mp.case_pp([world("reference"), world("b200")], feats, True, mp.Timer())
+    assert res["indices_identical"]
+    assert res["verdict"]["pass"], res["verdict"]
+
+
+def test_tgnet_fps_forward_backward_vs_reference():
+    mp = _model_parity()
+    feats, labels = mp.make_inputs(24000)
+    res = mp.case_tgn([world("reference"), world("b200")], feats, labels, mp.Timer())
+    assert res["indices_identical"]
+    assert res["tensors"]["nn_crop_indexes"]["bitwise"]
+    assert res["verdict"]["pass"], res["verdict"]
+    assert res["grads"]["pass"], res["grads"]

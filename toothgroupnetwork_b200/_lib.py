@@ -25,17 +25,54 @@ _SIGS = {
     "tgn_grouping_backward": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "tgn_interpolation_forward": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tgn_interpolation_backward": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "tgn_weighted_gather": [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "tgn_subtraction_forward": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tgn_subtraction_backward": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tgn_aggregation_forward": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "tgn_aggregation_backward": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tgn_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp],
     "tgn_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "tgn_three_nn_ex": [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "tgn_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "tgn_three_interpolate_ex": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "tgn_gather_rows": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "tgn_transpose_cn": [_i, _i, _i, _vp, _vp, _vp],
     "tgn_sa_group_mlp_max": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tgn_pw_pack_weights": [_i, _i, _vp, _vp, _vp],
+    "tgn_pw_layer_forward": [_vp, _vp],
+    "tgn_pw_apply": [_vp, _vp],
+    "tgn_pw_fill": [_vp, ctypes.c_longlong, _f, _vp],
 }
+
+
+
+class PwLayer(ctypes.Structure):
+    """tgn_pw_layer_t (include/tgn_b200.h)."""
+    _fields_ = [
+        ("rows", _i), ("rows_per_batch", _i), ("cin", _i), ("cout", _i), ("mode", _i),
+        ("seg_ptr", _vp * 2), ("seg_channels", _i * 2),
+        ("seg_batch_stride", ctypes.c_longlong * 2), ("seg_row_stride", ctypes.c_longlong * 2), ("seg_chan_stride", ctypes.c_longlong * 2),
+        ("xyz", _vp), ("feats", _vp), ("new_xyz", _vp), ("gidx", _vp),
+        ("N", _i), ("S", _i), ("K", _i), ("D", _i), ("xyz_first", _i),
+        ("in_affine", _i), ("in_update_running", _i),
+        ("in_stats", _vp), ("in_gamma", _vp), ("in_beta", _vp), ("in_running_mean", _vp), ("in_running_var", _vp),
+        ("in_eps", _f), ("in_momentum", _f),
+        ("w_packed", _vp), ("bias", _vp), ("y", _vp), ("stats", _vp), ("ymax", _vp), ("ymin", _vp),
+        ("group", _i), ("extrema_atomic", _i), ("precision", _i),
+    ]
+
+
+class PwApply(ctypes.Structure):
+    """tgn_pw_apply_t (include/tgn_b200.h)."""
+    _fields_ = [
+        ("rows", _i), ("rows_per_batch", _i), ("channels", _i), ("out_channels", _i), ("out_c_offset", _i), ("relu", _i),
+        ("src", _vp), ("ymin", _vp), ("out", _vp),
+        ("affine", _i), ("update_running", _i),
+        ("stats", _vp), ("stat_rows", ctypes.c_longlong),
+        ("gamma", _vp), ("beta", _vp), ("running_mean", _vp), ("running_var", _vp),
+        ("eps", _f), ("momentum", _f),
+    ]
+
 
 # the reference's ten extern "C" launchers (part 1): void return, legacy default stream
 REFERENCE_LAUNCHERS = [
@@ -45,7 +82,7 @@ REFERENCE_LAUNCHERS = [
     "subtraction_forward_cuda_launcher", "subtraction_backward_cuda_launcher",
     "aggregation_forward_cuda_launcher", "aggregation_backward_cuda_launcher",
 ]
-EXPORTS = list(_SIGS) + REFERENCE_LAUNCHERS + ["tgn_version", "tgn_last_error", "tgn_launch_count"]
+EXPORTS = list(_SIGS) + REFERENCE_LAUNCHERS + ["tgn_version", "tgn_last_error", "tgn_launch_count", "tgn_pw_packed_bytes", "tgn_pw_struct_size"]
 
 
 class TgnError(RuntimeError):
@@ -69,6 +106,12 @@ def load() -> ctypes.CDLL:
     lib.tgn_last_error.restype = ctypes.c_char_p
     lib.tgn_version.restype = _i
     lib.tgn_launch_count.restype = _i
+    lib.tgn_pw_packed_bytes.argtypes = [_i, _i]
+    lib.tgn_pw_packed_bytes.restype = ctypes.c_size_t
+    lib.tgn_pw_struct_size.argtypes = [_i]
+    lib.tgn_pw_struct_size.restype = _i
+    if lib.tgn_pw_struct_size(0) != ctypes.sizeof(PwLayer) or lib.tgn_pw_struct_size(1) != ctypes.sizeof(PwApply):
+        raise TgnError("ctypes mirror of tgn_pw_layer_t / tgn_pw_apply_t is out of date with include/tgn_b200.h")
     _lib = lib
     return lib
 

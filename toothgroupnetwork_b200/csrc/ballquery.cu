@@ -24,8 +24,15 @@ namespace {
 
 constexpr int kTile = 1024;   // points staged per shared-memory tile (16 KB as SoA x,y,z,|p|^2)
 
-__device__ __forceinline__ float sq_norm_unfused(float x, float y, float z) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+// |p|^2 as torch.sum(p ** 2, -1) rounds it ON THE GPU (square_distance :39-40), measured on B200 / torch 2.11
+// (scripts/diag_sumsq.py, profiles/r2_parity.md): a strided reduction (the permuted views the reference's modules
+// pass) accumulates in index order, (x*x + y*y) + z*z -- the same as torch on the CPU; a CONTIGUOUS (..., 3) tensor
+// (e.g. new_xyz fresh out of index_points) goes through the vectorised reduce path and comes out as
+// (x*x + z*z) + y*y.  `alt` selects the second form; the Python layer derives it from the layout the reference's
+// own call would see, per operand.
+__device__ __forceinline__ float sq_norm_unfused(float x, float y, float z, bool alt) {
+    return alt ? __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)), __fmul_rn(y, y))
+               : __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 __device__ __forceinline__ float sq_dist_expanded(float ax, float ay, float az, float an, float bx, float by, float bz,
                                                   float bn) {
@@ -40,12 +47,12 @@ __device__ __forceinline__ float sq_dist_expanded(float ax, float ay, float az, 
 // Stage points [base, base+cnt) of one cloud into shared SoA arrays (coalesced 12-byte reads).
 template <int THREADS>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ pts, int base, int cnt, float* sx, float* sy,
-                                           float* sz, float* sn)
+                                           float* sz, float* sn, bool alt)
 {
     for (int i = threadIdx.x; i < cnt; i += THREADS) {
         const float x = __ldg(pts + 3 * static_cast<size_t>(base + i)), y = __ldg(pts + 3 * static_cast<size_t>(base + i) + 1),
                     z = __ldg(pts + 3 * static_cast<size_t>(base + i) + 2);
-        sx[i] = x; sy[i] = y; sz[i] = z; sn[i] = sq_norm_unfused(x, y, z);
+        sx[i] = x; sy[i] = y; sz[i] = z; sn[i] = sq_norm_unfused(x, y, z, alt);
     }
     // pad to a multiple of 128 with points at infinite distance (never a member, never a neighbour)
     for (int i = cnt + threadIdx.x; i < ((cnt + 127) & ~127); i += THREADS) {
@@ -63,7 +70,7 @@ __device__ __forceinline__ uint64_t lds_f32x2(uint32_t addr) {      // two adjac
 template <int WARPS, typename IdxT>
 __global__ void __launch_bounds__(WARPS * 32)
 ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
-                  IdxT* __restrict__ group_idx, const int* __restrict__ answered)
+                  IdxT* __restrict__ group_idx, const int* __restrict__ answered, int order)
 {
     constexpr unsigned FULL = 0xffffffffu;
     if (answered && answered[blockIdx.y]) return;     // this cloud went through the grid kernel
@@ -78,7 +85,7 @@ ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__
     if (live) {
         const float* a = new_xyz + 3 * (static_cast<size_t>(b) * S + q);
         ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
-        an = sq_norm_unfused(ax, ay, az);
+        an = sq_norm_unfused(ax, ay, az, order & 1);
         row = group_idx + (static_cast<size_t>(b) * S + q) * nsample;
     }
     int cnt = live ? 0 : nsample;     // dead warps count as finished
@@ -87,7 +94,7 @@ ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__
     for (int base = 0; base < N; base += kTile) {
         const int tile = min(kTile, N - base);
         __syncthreads();              // previous tile fully consumed
-        stage_tile<WARPS * 32>(pts, base, tile, sx, sy, sz, sn);
+        stage_tile<WARPS * 32>(pts, base, tile, sx, sy, sz, sn, order & 2);
         __syncthreads();
         if (cnt < nsample) {
             // four 32-point steps per trip: 16 shared loads issued together, one early-exit test per 128
@@ -140,12 +147,12 @@ ball_query_kernel(int N, int S, float r2, int nsample, const float* __restrict__
 // ---- streaming variant (default) ------------------------------------------------------------------
 // pack: (x, y, z) -> (x, y, z, |p|^2) so that the scan needs ONE 16-byte load per point.
 __global__ void __launch_bounds__(256)
-pack_xyzn_kernel(size_t total, const float* __restrict__ xyz, float4* __restrict__ out)
+pack_xyzn_kernel(size_t total, const float* __restrict__ xyz, float4* __restrict__ out, int order)
 {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
-        out[i] = make_float4(x, y, z, sq_norm_unfused(x, y, z));
+        out[i] = make_float4(x, y, z, sq_norm_unfused(x, y, z, order & 2));
     }
 }
 
@@ -156,7 +163,7 @@ pack_xyzn_kernel(size_t total, const float* __restrict__ xyz, float4* __restrict
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 ball_query_stream_kernel(int N, int S, float r2, int nsample, const float4* __restrict__ pts, const float* __restrict__ new_xyz,
-                         IdxT* __restrict__ group_idx)
+                         IdxT* __restrict__ group_idx, int order)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,7 +172,7 @@ ball_query_stream_kernel(int N, int S, float r2, int nsample, const float4* __re
     if (q >= S) return;
     const float* a = new_xyz + 3 * (static_cast<size_t>(b) * S + q);
     const float ax = __ldg(a), ay = __ldg(a + 1), az = __ldg(a + 2);
-    const float an = sq_norm_unfused(ax, ay, az);
+    const float an = sq_norm_unfused(ax, ay, az, order & 1);
     IdxT* row = group_idx + (static_cast<size_t>(b) * S + q) * nsample;
     const float4* P = pts + static_cast<size_t>(b) * N;
     int cnt = 0, first = N;
@@ -197,7 +204,7 @@ ball_query_stream_kernel(int N, int S, float r2, int nsample, const float4* __re
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 three_nn_kernel(int N, int S, const float* __restrict__ xyz1, const float* __restrict__ xyz2, float* __restrict__ dist,
-                int* __restrict__ idx)
+                int* __restrict__ idx, int order)
 {
     __shared__ float sx[kTile], sy[kTile], sz[kTile], sn[kTile];
     const int b = blockIdx.y;
@@ -207,7 +214,7 @@ three_nn_kernel(int N, int S, const float* __restrict__ xyz1, const float* __res
     if (live) {
         const float* a = xyz1 + 3 * (static_cast<size_t>(b) * N + i);
         ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
-        an = sq_norm_unfused(ax, ay, az);
+        an = sq_norm_unfused(ax, ay, az, order & 1);
     }
     float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
     int i0 = 0, i1 = 0, i2 = 0;
@@ -215,7 +222,7 @@ three_nn_kernel(int N, int S, const float* __restrict__ xyz1, const float* __res
     for (int base = 0; base < S; base += kTile) {
         const int tile = min(kTile, S - base);
         __syncthreads();
-        stage_tile<THREADS>(pts, base, tile, sx, sy, sz, sn);
+        stage_tile<THREADS>(pts, base, tile, sx, sy, sz, sn, order & 2);
         __syncthreads();
         if (live) {
 #pragma unroll 4
@@ -240,7 +247,7 @@ three_nn_kernel(int N, int S, const float* __restrict__ xyz1, const float* __res
 // out[b,n,:] = sum_k w_k * points2[b, idx[b,n,k], :],  w = (1/(d+1e-8)) / sum (pointnet2_utils.py:337-340)
 __global__ void __launch_bounds__(256)
 three_interpolate_kernel(int N, int S, int C, const float* __restrict__ points2, const float* __restrict__ dist,
-                         const int* __restrict__ idx, float* __restrict__ out)
+                         const int* __restrict__ idx, float* __restrict__ out, bool norm_alt)
 {
     const int b = blockIdx.y;
     const size_t total = static_cast<size_t>(N) * C;
@@ -251,7 +258,9 @@ three_interpolate_kernel(int N, int S, int C, const float* __restrict__ points2,
         const size_t o = 3 * (static_cast<size_t>(b) * N + n);
         const float r0 = __fdiv_rn(1.0f, __fadd_rn(dist[o], 1e-8f)), r1 = __fdiv_rn(1.0f, __fadd_rn(dist[o + 1], 1e-8f)),
                     r2 = __fdiv_rn(1.0f, __fadd_rn(dist[o + 2], 1e-8f));
-        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        // torch.sum(dist_recip, dim=2) (:338): dist_recip is a fresh contiguous (B,N,3) tensor, so on CUDA the vectorised
+        // reduce applies, (r0 + r2) + r1; on the CPU (and in the committed fixtures) it is (r0 + r1) + r2
+        const float norm = norm_alt ? __fadd_rn(__fadd_rn(r0, r2), r1) : __fadd_rn(__fadd_rn(r0, r1), r2);
         const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
         float acc = __fmul_rn(p2[static_cast<size_t>(idx[o]) * C + c], w0);
         acc = __fadd_rn(acc, __fmul_rn(p2[static_cast<size_t>(idx[o + 1]) * C + c], w1));
@@ -273,6 +282,7 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
     if (N <= 0) { set_error("ball_query: N must be positive"); return TGN_ERR_INVALID; }
     if (B > 65535) { set_error("ball_query: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int order = (idx64 >> 4) & 3;      // bit 4: |new_xyz|^2 in the contiguous-reduce order, bit 5: |xyz|^2 likewise
     // Streaming variant (pack once into stream-ordered scratch, then fully independent warps).  Measured
     // on B200 it ties with the shared-memory tile kernel at 24k points (both issue-bound) and loses
     // to its packed-fp32x2 form, so it is only taken on request (idx64 bit 1 set: experiments).
@@ -283,12 +293,12 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
         const cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&packed), total * sizeof(float4), st);
         if (e == cudaSuccess) {
             const int pg = static_cast<int>(std::min<size_t>((total + 255) / 256, 16 * static_cast<size_t>(sm_count())));
-            pack_xyzn_kernel<<<pg, 256, 0, st>>>(total, xyz, packed);
+            pack_xyzn_kernel<<<pg, 256, 0, st>>>(total, xyz, packed, order);
             int rc = check_launch("pack_xyzn_kernel");
             if (rc == TGN_OK) {
                 dim3 grid((S + 7) / 8, B);
-                if (idx64 & 1) ball_query_stream_kernel<long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<long long*>(group_idx));
-                else ball_query_stream_kernel<int><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<int*>(group_idx));
+                if (idx64 & 1) ball_query_stream_kernel<long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<long long*>(group_idx), order);
+                else ball_query_stream_kernel<int><<<grid, 256, 0, st>>>(N, S, r2, nsample, packed, new_xyz, static_cast<int*>(group_idx), order);
                 rc = check_launch("ball_query_stream_kernel");
             }
             (void)cudaFreeAsync(packed, st);
@@ -314,7 +324,7 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
             ws.dim = reinterpret_cast<int4*>(grid_ws + reinterpret_cast<size_t>(ws.dim));
             ws.bnd = reinterpret_cast<float4*>(grid_ws + reinterpret_cast<size_t>(ws.bnd));
             ws.flag = reinterpret_cast<int*>(grid_ws + reinterpret_cast<size_t>(ws.flag));
-            const int rc = bq_grid_launch(B, N, S, r2, nsample, xyz, new_xyz, group_idx, (idx64 & 1) != 0, (idx64 & 8) ? 1 : 0, ws, st);
+            const int rc = bq_grid_launch(B, N, S, r2, nsample, xyz, new_xyz, group_idx, (idx64 & 1) != 0, (idx64 & 8) ? 1 : 0, order, ws, st);
             if (rc != TGN_OK) { (void)cudaFreeAsync(grid_ws, st); return rc; }
             answered = ws.flag;
         } else {
@@ -326,12 +336,12 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
     const bool wide = static_cast<long long>(B) * ((S + 15) / 16) >= 2LL * sm_count();
     if (wide) {
         dim3 grid((S + 15) / 16, B);
-        if (idx64 & 1) ball_query_kernel<16, long long><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx), answered);
-        else ball_query_kernel<16, int><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx), answered);
+        if (idx64 & 1) ball_query_kernel<16, long long><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx), answered, order);
+        else ball_query_kernel<16, int><<<grid, 512, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx), answered, order);
     } else {
         dim3 grid((S + 7) / 8, B);
-        if (idx64 & 1) ball_query_kernel<8, long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx), answered);
-        else ball_query_kernel<8, int><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx), answered);
+        if (idx64 & 1) ball_query_kernel<8, long long><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<long long*>(group_idx), answered, order);
+        else ball_query_kernel<8, int><<<grid, 256, 0, st>>>(N, S, r2, nsample, xyz, new_xyz, static_cast<int*>(group_idx), answered, order);
     }
     const int rc = check_launch("ball_query_kernel");
     if (grid_ws) (void)cudaFreeAsync(grid_ws, st);
@@ -340,24 +350,35 @@ int tgn_ball_query(int B, int N, int S, float r2, int nsample, const float* xyz,
 
 int tgn_three_nn(int B, int N, int S, const float* xyz1, const float* xyz2, float* dist, int* idx, void* stream)
 {
+    return tgn_three_nn_ex(B, N, S, xyz1, xyz2, dist, idx, 0, stream);
+}
+
+int tgn_three_nn_ex(int B, int N, int S, const float* xyz1, const float* xyz2, float* dist, int* idx, int order, void* stream)
+{
     using namespace tgn;
     if (B <= 0 || N <= 0) return TGN_OK;
     if (S < 3) { set_error("three_nn: needs at least 3 coarse points (S=%d)", S); return TGN_ERR_INVALID; }
     if (B > 65535) { set_error("three_nn: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
     dim3 grid((N + 127) / 128, B);
-    three_nn_kernel<128><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(N, S, xyz1, xyz2, dist, idx);
+    three_nn_kernel<128><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(N, S, xyz1, xyz2, dist, idx, order);
     return check_launch("three_nn_kernel");
 }
 
 int tgn_three_interpolate(int B, int N, int S, int C, const float* points2, const float* dist, const int* idx, float* out,
                           void* stream)
 {
+    return tgn_three_interpolate_ex(B, N, S, C, points2, dist, idx, out, 0, stream);
+}
+
+int tgn_three_interpolate_ex(int B, int N, int S, int C, const float* points2, const float* dist, const int* idx, float* out,
+                             int norm_alt, void* stream)
+{
     using namespace tgn;
     if (B <= 0 || N <= 0 || C <= 0) return TGN_OK;
     if (B > 65535) { set_error("three_interpolate: B=%d exceeds gridDim.y", B); return TGN_ERR_INVALID; }
     const size_t total = static_cast<size_t>(N) * C;
     const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 8 * static_cast<size_t>(sm_count())));
-    three_interpolate_kernel<<<dim3(blocks, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(N, S, C, points2, dist, idx, out);
+    three_interpolate_kernel<<<dim3(blocks, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(N, S, C, points2, dist, idx, out, norm_alt != 0);
     return check_launch("three_interpolate_kernel");
 }
 

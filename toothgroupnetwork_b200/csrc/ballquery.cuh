@@ -20,7 +20,8 @@ int bq_grid_max_points();
 // Byte size of the scratch; fills `offsets` with the byte offsets of the arrays (as pointers from 0).
 size_t bq_grid_workspace_bytes(int B, int N, BqGridWs* offsets);
 // force: 0 = per-cloud estimate decides, 1 = every cloud takes the grid kernel.
+// order: bit 0 / bit 1 = |new_xyz|^2 / |xyz|^2 rounded as torch's contiguous reduce does (see ballquery.cu).
 int bq_grid_launch(int B, int N, int S, float r2, int nsample, const float* xyz, const float* new_xyz, void* group_idx,
-                   bool idx64, int force, const BqGridWs& ws, cudaStream_t st);
+                   bool idx64, int force, int order, const BqGridWs& ws, cudaStream_t st);
 
 }  // namespace tgn

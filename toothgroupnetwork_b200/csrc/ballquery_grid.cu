@@ -37,8 +37,9 @@ constexpr int kMaxCells = 8192;      // 32 KB of shared-memory counters
 constexpr int kQW = 16;              // query warps per CTA
 constexpr unsigned FULL = 0xffffffffu;
 
-__device__ __forceinline__ float sq_norm_unfused(float x, float y, float z) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+__device__ __forceinline__ float sq_norm_unfused(float x, float y, float z, bool alt) {      // see ballquery.cu
+    return alt ? __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)), __fmul_rn(y, y))
+               : __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 __device__ __forceinline__ int float_ordered(float f) {
     const int i = __float_as_int(f);
@@ -106,19 +107,24 @@ bq_grid_estimate_kernel(int N, int S, float r2, int nsample, int force, const fl
             lo[a] = ordered_float(l); hi[a] = ordered_float(h);
         }
         float cs = fmaxf(sqrtf(fmaxf(r2, 0.f)), 1e-30f);
-        int nx, ny, nz;
-        for (;;) {
+        int nx = 0, ny = 0, nz = 0;
+        // bounded search (1e-30 * 1.26^700 > FLT_MAX); a non-finite extent (inf / NaN coordinates) never satisfies
+        // the exit test, so such a cloud is left to the tile kernel instead of spinning forever
+        bool found = false;
+        for (int it = 0; it < 700 && !found; ++it) {
             const float fx = (hi[0] - lo[0]) / cs, fy = (hi[1] - lo[1]) / cs, fz = (hi[2] - lo[2]) / cs;
             if (fx < 4096.f && fy < 4096.f && fz < 4096.f) {
                 nx = static_cast<int>(fx) + 1; ny = static_cast<int>(fy) + 1; nz = static_cast<int>(fz) + 1;
-                if (static_cast<long long>(nx) * ny * nz <= kEstCells) break;
+                if (static_cast<long long>(nx) * ny * nz <= kEstCells) found = true;
             }
-            cs *= 1.26f;
+            if (!found) cs *= 1.26f;
         }
+        if (!found) { nx = ny = nz = 0; ws.flag[b] = 0; }
         s_org = make_float4(lo[0], lo[1], lo[2], 1.0f / cs);
         s_dim = make_int4(nx, ny, nz, nx * ny * nz);
     }
     __syncthreads();
+    if (s_dim.w == 0) return;                        // block-uniform: flag[b] = 0 was written above
     const float4 org = s_org;
     const int4 dim = s_dim;
     for (int i = tid; i < ns; i += kET) {
@@ -155,7 +161,7 @@ bq_grid_estimate_kernel(int N, int S, float r2, int nsample, int force, const fl
 }
 
 __global__ void __launch_bounds__(kBT)
-bq_grid_build_kernel(int N, float r2, const float* __restrict__ xyz, BqGridWs ws)
+bq_grid_build_kernel(int N, float r2, const float* __restrict__ xyz, BqGridWs ws, int order)
 {
     __shared__ int cnt[kMaxCells];
     __shared__ int red[6][kBNW];
@@ -199,15 +205,17 @@ bq_grid_build_kernel(int N, float r2, const float* __restrict__ xyz, BqGridWs ws
         bn_max *= 1.000001f;
         // cells no smaller than the radius a query inside the cloud has to cover; coarser if the table overflows
         float cs = fmaxf(safe_radius(r2, bn_max, bn_max, cmax), 1e-30f);
-        int nx, ny, nz;
-        for (;;) {
+        int nx = 0, ny = 0, nz = 0;
+        bool found = false;                          // bounded like the estimate's search; see there
+        for (int it = 0; it < 700 && !found; ++it) {
             const float fx = (hi[0] - lo[0]) / cs, fy = (hi[1] - lo[1]) / cs, fz = (hi[2] - lo[2]) / cs;
             if (fx < 4096.f && fy < 4096.f && fz < 4096.f) {
                 nx = static_cast<int>(fx) + 1; ny = static_cast<int>(fy) + 1; nz = static_cast<int>(fz) + 1;
-                if (static_cast<long long>(nx) * ny * nz <= kMaxCells) break;
+                if (static_cast<long long>(nx) * ny * nz <= kMaxCells) found = true;
             }
-            cs *= 1.26f;
+            if (!found) cs *= 1.26f;
         }
+        if (!found) { nx = ny = nz = 0; ws.flag[b] = 0; }      // non-finite extent: the tile kernel answers this cloud
         s_org = make_float4(lo[0], lo[1], lo[2], 1.0f / cs);
         s_dim = make_int4(nx, ny, nz, nx * ny * nz);
         ws.org[b] = s_org;
@@ -217,6 +225,7 @@ bq_grid_build_kernel(int N, float r2, const float* __restrict__ xyz, BqGridWs ws
     __syncthreads();
     const float4 org = s_org;
     const int4 dim = s_dim;
+    if (dim.w == 0) return;                          // block-uniform: cloud handed to the tile kernel (flag[b] = 0)
 
     // ---- histogram --------------------------------------------------------------------------------------
     for (int j = tid; j < N; j += kBT) {
@@ -280,7 +289,7 @@ bq_grid_build_kernel(int N, float r2, const float* __restrict__ xyz, BqGridWs ws
         const size_t u = static_cast<size_t>(pos >> 1);
         const int h = pos & 1;
         ga[4 * u + h] = x; ga[4 * u + 2 + h] = y;
-        gb[4 * u + h] = z; gb[4 * u + 2 + h] = sq_norm_unfused(x, y, z);
+        gb[4 * u + h] = z; gb[4 * u + 2 + h] = sq_norm_unfused(x, y, z, order & 2);
         gj[2 * u + h] = j;
     }
 }
@@ -288,7 +297,7 @@ bq_grid_build_kernel(int N, float r2, const float* __restrict__ xyz, BqGridWs ws
 template <typename IdxT>
 __global__ void __launch_bounds__(kQW * 32)
 ball_query_grid_kernel(int N, int S, float r2, int nsample, const float* __restrict__ new_xyz, IdxT* __restrict__ group_idx,
-                       BqGridWs ws, int rows, int qpw)
+                       BqGridWs ws, int rows, int qpw, int order)
 {
     extern __shared__ unsigned bm_all[];            // [kQW][32 * rows] membership bitmaps over original indices
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -312,7 +321,7 @@ ball_query_grid_kernel(int N, int S, float r2, int nsample, const float* __restr
         if (q >= S) break;
         const float* a = new_xyz + 3 * (static_cast<size_t>(b) * S + q);
         const float ax = __ldg(a), ay = __ldg(a + 1), az = __ldg(a + 2);
-        const float an = sq_norm_unfused(ax, ay, az);
+        const float an = sq_norm_unfused(ax, ay, az, order & 1);
         const uint64_t AX = pack2(ax, ax), AY = pack2(ay, ay), AZ = pack2(az, az), AN = pack2(an, an);
         IdxT* row = group_idx + (static_cast<size_t>(b) * S + q) * nsample;
         const float R = safe_radius(r2, an, bnd.x, fmaxf(bnd.y, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az)))));
@@ -422,31 +431,26 @@ size_t bq_grid_workspace_bytes(int B, int N, BqGridWs* ws_offsets)
 int bq_grid_max_points() { return 32 * 32 * ((200 * 1024) / (kQW * 32 * 4)); }
 
 int bq_grid_launch(int B, int N, int S, float r2, int nsample, const float* xyz, const float* new_xyz, void* group_idx,
-                   bool idx64, int force, const BqGridWs& ws, cudaStream_t st)
+                   bool idx64, int force, int order, const BqGridWs& ws, cudaStream_t st)
 {
     bq_grid_estimate_kernel<<<B, kET, 0, st>>>(N, S, r2, nsample, force, xyz, ws);
     int rc = check_launch("bq_grid_estimate_kernel");
     if (rc != TGN_OK) return rc;
-    bq_grid_build_kernel<<<B, kBT, 0, st>>>(N, r2, xyz, ws);
+    bq_grid_build_kernel<<<B, kBT, 0, st>>>(N, r2, xyz, ws, order);
     rc = check_launch("bq_grid_build_kernel");
     if (rc != TGN_OK) return rc;
     const int rows = ((N + 31) / 32 + 31) / 32;     // bitmap rows of 32 words
     const size_t smem = static_cast<size_t>(kQW) * 32 * rows * sizeof(unsigned);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ball_query_grid_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(ball_query_grid_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
-        configured = smem;
-    }
+    rc = idx64 ? ensure_dynamic_smem(reinterpret_cast<const void*>(ball_query_grid_kernel<long long>), smem)
+               : ensure_dynamic_smem(reinterpret_cast<const void*>(ball_query_grid_kernel<int>), smem);
+    if (rc != TGN_OK) return rc;
     // queries per warp: 4, more when the batch alone fills the machine (fewer, longer CTAs: clouds the
     // estimate left to the tile kernel cost one early-exit CTA launch per block of queries)
     const long long blocks4 = static_cast<long long>(B) * ((S + kQW * 4 - 1) / (kQW * 4));
     const int qpw = 4 * static_cast<int>(std::max<long long>(1, std::min<long long>(blocks4 / (12LL * sm_count()), 16)));
     dim3 grid((S + kQW * qpw - 1) / (kQW * qpw), B);
-    if (idx64) ball_query_grid_kernel<long long><<<grid, kQW * 32, smem, st>>>(N, S, r2, nsample, new_xyz, static_cast<long long*>(group_idx), ws, rows, qpw);
-    else ball_query_grid_kernel<int><<<grid, kQW * 32, smem, st>>>(N, S, r2, nsample, new_xyz, static_cast<int*>(group_idx), ws, rows, qpw);
+    if (idx64) ball_query_grid_kernel<long long><<<grid, kQW * 32, smem, st>>>(N, S, r2, nsample, new_xyz, static_cast<long long*>(group_idx), ws, rows, qpw, order);
+    else ball_query_grid_kernel<int><<<grid, kQW * 32, smem, st>>>(N, S, r2, nsample, new_xyz, static_cast<int*>(group_idx), ws, rows, qpw, order);
     return check_launch("ball_query_grid_kernel");
 }
 

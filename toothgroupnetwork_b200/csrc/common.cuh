@@ -13,7 +13,8 @@ namespace tgn {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> status (+ message)
-int sm_count();
+int sm_count();                       // of the current device (cached per device)
+int ensure_dynamic_smem(const void* func, size_t bytes);   // per (device, kernel) opt-in to > 48 KB of dynamic shared memory
 void keep_async_pool();               // configure the default cudaMallocAsync pool to cache freed scratch
 
 // ---------------------------------------------------------------- packed fp32x2 (FADD2/FMUL2/FFMA2)

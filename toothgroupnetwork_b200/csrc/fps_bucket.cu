@@ -533,12 +533,8 @@ template <int MT_>
 int launch_main(int b, size_t smem, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
                 const BucketWs& ws, int bs_log2, cudaStream_t stream)
 {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        const cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
-        configured = smem;
-    }
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(fps_bucket_kernel<MT_>), smem);
+    if (rc_attr != TGN_OK) return rc_attr;
     fps_bucket_kernel<MT_><<<b, MT_, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
     return check_launch("fps_bucket_kernel");
 }
@@ -579,12 +575,8 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
     if (n_max <= kSmemSortMaxN) {
         const int spad = (n_max + 31) & ~31;
         const size_t sort_smem = 2 * sizeof(unsigned) * static_cast<size_t>(spad);
-        static bool sort_attr = false;
-        if (!sort_attr) {
-            cudaFuncSetAttribute(fps_bucket_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(2 * sizeof(unsigned) * kSmemSortMaxN));
-            sort_attr = true;
-        }
+        const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(fps_bucket_sort_kernel<true>), 2 * sizeof(unsigned) * kSmemSortMaxN);
+        if (rc_attr != TGN_OK) return rc_attr;
         fps_bucket_sort_kernel<true><<<b, kT, sort_smem, stream>>>(xyz, offset, tmp, ws, bs_log2, spad);
     } else {
         fps_bucket_sort_kernel<false><<<b, kT, 0, stream>>>(xyz, offset, tmp, ws, bs_log2, 0);

@@ -57,7 +57,7 @@ rows_scatter_add_kernel(size_t rows, int c, const float* __restrict__ grad_out, 
 // (interpolation_cuda_kernel.cu:5-18; the reference's "+=" contracts to FFMA).
 __global__ void __launch_bounds__(256)
 interp_forward_kernel(int n, int c, int k, const float* __restrict__ in, const int* __restrict__ idx,
-                      const float* __restrict__ w, float* __restrict__ out)
+                      const float* __restrict__ w, float* __restrict__ out, bool fused)
 {
     const size_t total = static_cast<size_t>(n) * c;
     for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
@@ -65,8 +65,13 @@ interp_forward_kernel(int n, int c, int k, const float* __restrict__ in, const i
         const size_t p = e / c;
         const int ch = static_cast<int>(e - p * c);
         float acc = out[e];
-        for (int i = 0; i < k; ++i)
-            acc = __fmaf_rn(__ldg(in + static_cast<size_t>(__ldg(idx + p * k + i)) * c + ch), __ldg(w + p * k + i), acc);
+        if (fused) {
+            for (int i = 0; i < k; ++i)
+                acc = __fmaf_rn(__ldg(in + static_cast<size_t>(__ldg(idx + p * k + i)) * c + ch), __ldg(w + p * k + i), acc);
+        } else {      // pointops.interpolation (pointops.py:177-179) accumulates with torch ops: product rounded, then added
+            for (int i = 0; i < k; ++i)
+                acc = __fadd_rn(acc, __fmul_rn(__ldg(in + static_cast<size_t>(__ldg(idx + p * k + i)) * c + ch), __ldg(w + p * k + i)));
+        }
         out[e] = acc;
     }
 }
@@ -290,7 +295,14 @@ int tgn_grouping_backward(int m, int nsample, int c, const float* grad_output, c
 int tgn_interpolation_forward(int n, int c, int k, const float* input, const int* idx, const float* weight, float* output, void* stream)
 {
     if (n <= 0 || c <= 0) return TGN_OK;
-    interp_forward_kernel<<<grid_for(static_cast<size_t>(n) * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, c, k, input, idx, weight, output);
+    interp_forward_kernel<<<grid_for(static_cast<size_t>(n) * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, c, k, input, idx, weight, output, true);
+    return check_launch("interp_forward_kernel");
+}
+
+int tgn_weighted_gather(int n, int c, int k, const float* input, const int* idx, const float* weight, float* output, int fused, void* stream)
+{
+    if (n <= 0 || c <= 0) return TGN_OK;
+    interp_forward_kernel<<<grid_for(static_cast<size_t>(n) * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, c, k, input, idx, weight, output, fused != 0);
     return check_launch("interp_forward_kernel");
 }
 

@@ -200,12 +200,8 @@ int sa_mlp_fp32_launch(SaParams p, cudaStream_t st)
     p.wt_floats = p.wt_resident ? wsum : ((wmax + 3) & ~3);
     const size_t smem = fixed + static_cast<size_t>(p.wt_floats) * sizeof(float);
     if (smem > 227 * 1024) { set_error("sa_group_mlp_max: %zu bytes of shared memory needed", smem); return TGN_ERR_INVALID; }
-    static size_t configured = 0;
-    if (smem > configured) {
-        const cudaError_t e = cudaFuncSetAttribute(sa_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
-        configured = smem;
-    }
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(sa_mlp_fp32_kernel), smem);
+    if (rc_attr != TGN_OK) return rc_attr;
     if (p.K <= kRowsMax) {
         p.gpt = kRowsMax / p.K;
         p.chunks = 1;

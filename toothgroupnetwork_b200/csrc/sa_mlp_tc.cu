@@ -503,12 +503,8 @@ int sa_mlp_tc_launch(SaParams p, cudaStream_t st)
 {
     TcLayout lay{};
     if (!make_layout(p, lay)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
-    static uint32_t configured = 0;
-    if (lay.total > configured) {
-        const cudaError_t e = cudaFuncSetAttribute(sa_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lay.total));
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
-        configured = lay.total;
-    }
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(sa_mlp_tc_kernel), lay.total);
+    if (rc_attr != TGN_OK) return rc_attr;
     // one persistent CTA (4 tile groups, the whole TMEM budget of its accumulators) per SM
     const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
     const int grid = static_cast<int>(std::min<long long>((tiles + kGroups - 1) / kGroups, sm_count()));

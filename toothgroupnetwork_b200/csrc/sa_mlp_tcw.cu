@@ -380,12 +380,8 @@ bool make_wlayout(const SaParams& p, WLayout& lay)
 template <int kGroups>
 int launch_tcw(const SaParams& p, const WLayout& lay, cudaStream_t st)
 {
-    static uint32_t configured = 0;
-    if (lay.total > configured) {
-        const cudaError_t e = cudaFuncSetAttribute(sa_mlp_tcw_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lay.total));
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return TGN_ERR_CUDA; }
-        configured = lay.total;
-    }
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(sa_mlp_tcw_kernel<kGroups>), lay.total);
+    if (rc_attr != TGN_OK) return rc_attr;
     const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
     const int grid = static_cast<int>(std::min<long long>((tiles + kGroups - 1) / kGroups, sm_count()));
     sa_mlp_tcw_kernel<kGroups><<<grid, kRows * kGroups, lay.total, st>>>(p, lay);

@@ -83,6 +83,8 @@ class HostPipeline:
             with torch.cuda.stream(s):
                 d = dev[lo:hi]
                 new_xyz, new_points = self.module(d[:, :3].contiguous(), d)
+                if not new_xyz.is_contiguous():        # the modules return the reference's permuted view of (B,S,3)
+                    new_xyz = pn2.transpose_last2(new_xyz.permute(0, 2, 1))
                 done = torch.cuda.Event()
                 done.record(s)
             self.copy_out.wait_event(done)

@@ -38,7 +38,7 @@ def fps_packed(xyz: torch.Tensor, offset: torch.Tensor, new_offset: torch.Tensor
     _need(xyz, torch.float32, "xyz")
     _need(offset, torch.int32, "offset")
     _need(new_offset, torch.int32, "new_offset")
-    idx = _empty((m_total,), torch.int32, xyz)
+    idx = torch.zeros((m_total,), dtype=torch.int32, device=xyz.device)   # zero-filled like the reference (:21)
     if m_total == 0:
         return idx
     tmp = None
@@ -49,17 +49,24 @@ def fps_packed(xyz: torch.Tensor, offset: torch.Tensor, new_offset: torch.Tensor
     return idx
 
 
+def _offset_sizes(offset: torch.Tensor, new_offset: torch.Tensor, n_total: int) -> Tuple[int, int]:
+    """(largest segment, total samples) of an (offset, new_offset) pair: ONE host copy of both vectors, where the
+    reference reads them back with one blocking ``.item()`` per cloud (:18-21).  The output size is data, so one
+    read-back is the floor for this signature; its callers (``blocks.py:64-69``) have just synchronised on
+    ``o[i].item()`` themselves.  Callers that know the sizes use ``fps_packed`` directly and never synchronise."""
+    host = torch.stack([offset.to(torch.int64), new_offset.to(torch.int64)]).cpu()
+    n_max = int(torch.diff(host[0], prepend=host[0].new_zeros(1)).max())
+    return n_max, int(host[1][-1])
+
+
 class FurthestSampling(Function):
     """:10-27.  input: xyz (n,3), offset (b), new_offset (b); output: idx (m) int32 global row ids."""
 
     @staticmethod
     def forward(ctx, xyz, offset, new_offset):
-        # one host copy of the two offset vectors (the reference syncs once per cloud, :18-21)
-        host = torch.stack([offset.to(torch.int64), new_offset.to(torch.int64)]).cpu()
-        if host.shape[1] == 0:
+        if offset.shape[0] == 0:
             return _empty((0,), torch.int32, xyz)
-        n_max = int(torch.diff(host[0], prepend=host[0].new_zeros(1)).max())
-        m_total = int(host[1][-1])
+        n_max, m_total = _offset_sizes(offset, new_offset, xyz.shape[0])
         idx = fps_packed(xyz, offset, new_offset, n_max, m_total)
         ctx.mark_non_differentiable(idx)
         return idx
@@ -217,14 +224,14 @@ class _WeightedGather(Function):
     """out[n,:] = sum_i input[idx[n,i],:] * weight[n,i] with a scatter-add backward wrt input."""
 
     @staticmethod
-    def forward(ctx, input, idx, weight):
+    def forward(ctx, input, idx, weight, fused=True):
         _need(input, torch.float32, "input")
         _need(idx, torch.int32, "idx")
         _need(weight, torch.float32, "weight")
         n, k = idx.shape
         m, c = input.shape
         out = torch.zeros((n, c), dtype=torch.float32, device=input.device)
-        L.call("tgn_interpolation_forward", n, c, k, L.ptr(input), L.ptr(idx), L.ptr(weight), L.ptr(out), L.stream_ptr())
+        L.call("tgn_weighted_gather", n, c, k, L.ptr(input), L.ptr(idx), L.ptr(weight), L.ptr(out), 1 if fused else 0, L.stream_ptr())
         ctx.m = m
         ctx.save_for_backward(idx, weight)
         return out
@@ -236,7 +243,7 @@ class _WeightedGather(Function):
         n, c = grad_output.shape
         gi = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad_output.device)
         L.call("tgn_interpolation_backward", n, c, idx.shape[1], L.ptr(grad_output), L.ptr(idx), L.ptr(weight), L.ptr(gi), L.stream_ptr())
-        return gi, None, None
+        return gi, None, None, None
 
 
 def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
@@ -245,7 +252,7 @@ def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
     assert xyz.is_contiguous() and new_xyz.is_contiguous() and feat.is_contiguous()
     idx, dist = knnquery(k, xyz, new_xyz, offset, new_offset)
     weight = _inverse_distance_weights(dist).detach().contiguous()
-    return _WeightedGather.apply(feat, idx, weight)
+    return _WeightedGather.apply(feat, idx, weight, False)      # the reference accumulates with torch ops here: unfused (:177-179)
 
 
 class Interpolation(Function):
