@@ -91,6 +91,21 @@ int tgn_furthestsampling(int b, int n_max, const float *xyz, const int *offset, 
 int tgn_knnquery(int b, int m, int nsample, const float *xyz, const float *new_xyz, const int *offset,
                  const int *new_offset, int *idx, float *dist2, void *stream);
 
+/* Crop extraction: the k (<= 4096) nearest points of each of Q centres per cloud, ascending (float64 distance, index) --
+ * replaces ops_utils.get_nearest_neighbor_idx (sklearn KDTree.query(k=3072) on the host, ops_utils.py:146-161).
+ * xyz (B,N,3), centres (B,Q,3) -> out_idx (B,Q,k) int32, or int64 when idx64 != 0.  One CTA per centre: radix select of
+ * the k-th distance, compaction, bitonic sort. */
+int tgn_crop_knn(int B, int N, int Q, int k, const float *xyz, const float *centres, void *out_idx, int idx64, void *stream);
+
+/* kNN through a per-segment uniform grid: identical answers to tgn_knnquery (distinct distances: order-independent;
+ * ties among the k+1 best: the query is re-run with the reference's index-order heap), ~100x fewer distance evaluations
+ * on 24k-point clouds.  The grid depends only on (xyz, offset): build it once into a caller-owned DEVICE workspace of
+ * tgn_knn_grid_bytes(b, n_total) bytes and reuse it for every query set / k against that point set. */
+size_t tgn_knn_grid_bytes(int b, int n_total);
+int tgn_knn_grid_build(int b, int n_total, const float *xyz, const int *offset, void *workspace, void *stream);
+int tgn_knn_grid_query(int b, int n_total, int m, int nsample, const float *xyz, const float *new_xyz, const int *offset,
+                       const int *new_offset, const void *workspace, int *idx, float *dist2, void *stream);
+
 int tgn_grouping_forward(int m, int nsample, int c, const float *input, const int *idx, float *output, void *stream);
 int tgn_grouping_backward(int m, int nsample, int c, const float *grad_output, const int *idx, float *grad_input, void *stream);
 int tgn_interpolation_forward(int n, int c, int k, const float *input, const int *idx, const float *weight, float *output, void *stream);
@@ -99,6 +114,22 @@ int tgn_interpolation_backward(int n, int c, int k, const float *grad_output, co
  * (== tgn_interpolation_forward); fused = 0: product rounded, then added -- the arithmetic of the torch loop in
  * pointops.interpolation (pointops.py:177-179), which is what the models call. */
 int tgn_weighted_gather(int n, int c, int k, const float *input, const int *idx, const float *weight, float *output, int fused, void *stream);
+/* Deterministic, ORDER-EXACT scatter-add backwards.  The reference's live callers gather with torch advanced indexing,
+ * whose backward (index_put_ accumulate) adds every destination row's contributions sequentially in ascending source
+ * position.  tgn_csr_build inverts an index tensor once (keys[M] -> per destination row the ascending list of source
+ * positions) into a DEVICE workspace of tgn_csr_bytes(M, n_rows); the two backwards below then reproduce torch's sums
+ * bit for bit, without value atomics.
+ *   tgn_gather_backward_det:           grad_in[r,:] = sum_{p : keys[p]=r, ascending} grad_out[p,:]      (grad_out (M,c))
+ *   tgn_weighted_gather_backward_det:  keys = idx (n,k) flattened; grad_out (n,c), weight (n,k):
+ *        per i: G_i[r,:] = sum_{n ascending, idx[n,i]=r} grad_out[n,:]*weight[n,i];  grad_in = ((G_{k-1}+G_{k-2})+...)+G_0
+ *        -- the order in which autograd sums the k index_put results of pointops.interpolation (pointops.py:177-179);
+ *        single != 0: one accumulation over all (n,i) in ascending n*k+i -- the backward of pointnet2_utils.py:340. */
+size_t tgn_csr_bytes(long long M, int n_rows);
+int tgn_csr_build(long long M, int n_rows, const int *keys, void *workspace, void *stream);
+int tgn_gather_backward_det(long long M, int n_rows, int c, const void *workspace, const float *grad_out, float *grad_in, void *stream);
+int tgn_weighted_gather_backward_det(long long M, int n_rows, int c, int k, int single, const void *workspace, const float *grad_out,
+                                     const float *weight, float *grad_in, void *stream);
+
 int tgn_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2, const int *idx, float *output, void *stream);
 int tgn_subtraction_backward(int n, int nsample, int c, const int *idx, const float *grad_output, float *grad_input1, float *grad_input2, void *stream);
 int tgn_aggregation_forward(int n, int nsample, int c, int w_c, const float *input, const float *position, const float *weight,

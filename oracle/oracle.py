@@ -381,3 +381,30 @@ def sa_sample_and_search_batch(xyz, npoint, radius, nsample):
     lib().oracle_sa_sample_and_search_batch(B, N, int(npoint), ctypes.c_float(float(radius_sq_f32(radius))), int(nsample),
                                             _p(xyz, _f32p), _p(fps, _i64p), _p(new_xyz, _f32p), _p(gidx, _i64p))
     return fps, new_xyz, gidx
+
+
+def sa_group_mlp_max_batch(xyz, feats, new_xyz, gidx, layers: Sequence[MlpParams]):
+    """Grouped MLP (eval-mode BatchNorm) + max for a batch, one cloud per OpenMP thread (bench.py's CPU baseline and
+    its parity checker).  xyz (B,N,3), feats (B,N,D) point-major or None, new_xyz (B,S,3), gidx (B,S,K) int64
+    -> (B, C_out, S) float32; channel order of a group is [xyz_rel, feats] (pointnet2_utils.py:169)."""
+    xyz, new_xyz = _f(xyz), _f(new_xyz)
+    gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+    B, N, _ = xyz.shape
+    S, K = gidx.shape[1], gidx.shape[2]
+    D = 0 if feats is None else feats.shape[2]
+    f = None if feats is None else _f(feats)
+    ch = [3 + D] + [int(p.weight.shape[0]) for p in layers]
+    wts, scs, shs = [], [], []
+    for p in layers:
+        w = p.weight.detach().double().numpy()
+        scale = (p.gamma.double() / torch.sqrt(p.var.double() + p.eps)).numpy()
+        shift = (p.beta.double() - p.mean.double() * torch.from_numpy(scale)).numpy() + scale * p.bias.double().numpy()
+        wts.append(_f(w.T))
+        scs.append(_f(scale))
+        shs.append(_f(shift))
+    arr = lambda xs: (ctypes.POINTER(ctypes.c_float) * len(xs))(*[_p(x, _f32p) for x in xs])
+    chv = (ctypes.c_int * len(ch))(*ch)
+    out = np.empty((B, ch[-1], S), np.float32)
+    lib().oracle_sa_group_mlp_max_batch(B, N, S, K, D, _p(xyz, _f32p), None if f is None else _p(f, _f32p), _p(new_xyz, _f32p),
+                                        _p(gidx, _i64p), len(layers), chv, arr(wts), arr(scs), arr(shs), _p(out, _f32p))
+    return out

@@ -381,3 +381,72 @@ void oracle_sa_sample_and_search_batch(int B, int n, int npoint, float r2, int n
         oracle_query_ball_point(n, npoint, r2, nsample, cx, cn, group_idx + (size_t)b * npoint * nsample);
     }
 }
+
+/* Grouped shared MLP + max of one set-abstraction level for a batch of clouds, one cloud per OpenMP thread
+ * (PointNetSetAbstraction.forward pointnet2_utils.py:227-237 with eval-mode BatchNorm): for every sampled centre s
+ * gather its K neighbours as rows [xyz - centre | feats] (:163-169), run L x (1x1 conv + BatchNorm + ReLU) on the
+ * (K, C) tile while it is cache-resident, keep the max over the K rows.  Weights arrive TRANSPOSED (wt[l]: (C_l, C_{l+1})
+ * row-major) with BatchNorm given as per-channel scale / shift applied after the convolution (y = scale*(Wx) + shift,
+ * shift already holding scale*bias), so that the inner loop is a vectorisable axpy over output channels.
+ * This is the CPU baseline's MLP leg (bench.py) -- contiguous tiles, per-cloud threads: it scales with cores, unlike
+ * running the reference's permuted (B,C,K,S) tensor through whole-tensor passes. */
+__attribute__((target_clones("arch=skylake-avx512", "arch=haswell", "default")))
+static void sa_mlp_max_cloud(int n, int S, int K, int D, const float *xyz, const float *feats, const float *new_xyz,
+                             const int64_t *gidx, int L, const int *ch, const float *const *wt, const float *const *scale,
+                             const float *const *shift, float *out /* (C_out, S) */, float *buf0, float *buf1)
+{
+    const int c0 = ch[0], cl = ch[L];
+    for (int s = 0; s < S; ++s) {
+        float *x = buf0, *y = buf1;
+        for (int k = 0; k < K; ++k) {
+            const int64_t j = gidx[(size_t)s * K + k];
+            float *row = x + (size_t)k * c0;
+            if (j < 0 || j >= n) { for (int c = 0; c < c0; ++c) row[c] = 0.f; continue; }
+            for (int a = 0; a < 3; ++a) row[a] = xyz[3 * (size_t)j + a] - new_xyz[3 * (size_t)s + a];
+            for (int d = 0; d < D; ++d) row[3 + d] = feats[(size_t)j * D + d];
+        }
+        for (int l = 0; l < L; ++l) {
+            const int ci = ch[l], co = ch[l + 1];
+            const float *w = wt[l], *sc = scale[l], *sh = shift[l];
+            for (int k = 0; k < K; ++k) {
+                const float *xi = x + (size_t)k * ci;
+                float *yo = y + (size_t)k * co;
+                for (int o = 0; o < co; ++o) yo[o] = 0.f;
+                for (int c = 0; c < ci; ++c) {
+                    const float xv = xi[c];
+                    const float *wr = w + (size_t)c * co;
+                    for (int o = 0; o < co; ++o) yo[o] += xv * wr[o];
+                }
+                for (int o = 0; o < co; ++o) {
+                    const float v = yo[o] * sc[o] + sh[o];
+                    yo[o] = v > 0.f ? v : 0.f;
+                }
+            }
+            float *t = x; x = y; y = t;
+        }
+        for (int o = 0; o < cl; ++o) {
+            float m = x[o];
+            for (int k = 1; k < K; ++k) { const float v = x[(size_t)k * cl + o]; m = v > m ? v : m; }
+            out[(size_t)o * S + s] = m;
+        }
+    }
+}
+
+void oracle_sa_group_mlp_max_batch(int B, int n, int S, int K, int D, const float *xyz, const float *feats,
+                                   const float *new_xyz, const int64_t *gidx, int L, const int *ch,
+                                   const float *const *wt, const float *const *scale, const float *const *shift, float *out)
+{
+    int cmax = 0;
+    for (int l = 0; l <= L; ++l) cmax = ch[l] > cmax ? ch[l] : cmax;
+#pragma omp parallel
+    {
+        float *buf0 = (float *)malloc(sizeof(float) * (size_t)K * cmax), *buf1 = (float *)malloc(sizeof(float) * (size_t)K * cmax);
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; ++b)
+            sa_mlp_max_cloud(n, S, K, D, xyz + (size_t)b * n * 3, feats ? feats + (size_t)b * n * D : NULL,
+                             new_xyz + (size_t)b * S * 3, gidx + (size_t)b * S * K, L, ch, wt, scale, shift,
+                             out + (size_t)b * ch[L] * S, buf0, buf1);
+        free(buf0);
+        free(buf1);
+    }
+}

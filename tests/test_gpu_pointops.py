@@ -167,6 +167,60 @@ def test_knn_matches_reference_kernel(name, build, m, off, noff, k):
     assert np.array_equal(w_idx, r_idx.cpu().numpy()) and np.array_equal(w_d2.view(np.uint32), r_d2.cpu().numpy().view(np.uint32))
 
 
+GRID_CASES = [
+    # name, cloud builder, offsets, query builder (None = self), new offsets, k
+    ("arch24k_self_k36", lambda: clouds.dental_arch(24000, 1)[0], [24000], None, None, 36),
+    ("arch24k_self_k24", lambda: clouds.dental_arch(24000, 2)[0], [24000], None, None, 24),
+    ("down_6000_from_24k_k24", lambda: clouds.dental_arch(24000, 3)[0], [24000], lambda x: x[::4].contiguous(), [6000], 24),
+    ("up_24k_from_6000_k3", lambda: clouds.dental_arch(24000, 4)[0][::4].contiguous(), [6000], lambda x: clouds.dental_arch(24000, 4)[0], [24000], 3),
+    ("up_24k_from_6000_k1", lambda: clouds.dental_arch(24000, 5)[0][::4].contiguous(), [6000], lambda x: clouds.dental_arch(24000, 5)[0], [24000], 1),
+    ("crops_16x3072_self_k36", lambda: torch.cat([clouds.dental_arch(3072, 10 + j)[0] for j in range(16)]), [3072 * (j + 1) for j in range(16)], None, None, 36),
+    ("ragged_segments_k24", lambda: torch.cat([clouds.cube(n, 30 + n) for n in (12, 3000, 1, 5000, 700)]), list(np.cumsum([12, 3000, 1, 5000, 700])), None, None, 24),
+    ("duplicated_vertices_k8", lambda: clouds.with_duplicates(clouds.cube(4096, 4), 4), [8192], None, None, 8),
+    ("duplicated_vertices_k36", lambda: clouds.with_duplicates(clouds.dental_arch(6000, 6)[0], 5), [12000], None, None, 36),
+    ("queries_outside_the_cloud_k16", lambda: clouds.cube(8000, 7) * 0.2, [8000], lambda x: clouds.cube(2000, 8) * 3.0, [2000], 16),
+    ("flat_cloud_k16", lambda: clouds.cube(6000, 9) * torch.tensor([1.0, 1.0, 0.0]), [6000], None, None, 16),
+    ("all_points_equal_k8", lambda: torch.ones(3000, 3), [3000], None, None, 8),
+    ("k100", lambda: clouds.dental_arch(9000, 11)[0], [9000], None, None, 100),
+]
+
+
+@pytest.mark.parametrize("name,build,off,qbuild,noff,k", GRID_CASES, ids=[c[0] for c in GRID_CASES])
+def test_knn_grid_equals_bruteforce_kernel_and_reference(name, build, off, qbuild, noff, k):
+    """The uniform-grid search (csrc/knn_grid.cu) against the brute-force warp kernel (csrc/knn.cu), bit for bit --
+    indices including the reference's tie order -- and against the verbatim reference kernel when it is present."""
+    xyz = build().contiguous()
+    q = xyz if qbuild is None else qbuild(xyz).contiguous()
+    o, no = i32(np.asarray(off, np.int32)), i32(np.asarray(off if noff is None else noff, np.int32))
+    x, qq = xyz.cuda(), q.cuda()
+    pointops.clear_knn_caches()
+    pointops.set_knn_grid(False)
+    try:
+        b_idx, b_d2 = pointops.knn_packed(k, x, qq, o, no)
+    finally:
+        pointops.set_knn_grid(True)
+    launches = L.launch_count()
+    g_idx, g_d2 = pointops.knn_packed(k, x, qq, o, no)
+    assert L.launch_count() - launches == 5        # four build kernels + the query
+    assert torch.equal(g_d2.view(torch.int32), b_d2.view(torch.int32))
+    assert torch.equal(g_idx, b_idx)
+    launches = L.launch_count()
+    c_idx, c_d2 = pointops.knn_packed(k, x, qq, o, no)           # identical repeated query: served from the cache
+    assert L.launch_count() == launches and c_idx is g_idx
+    k2 = k // 2 if k > 1 else 2
+    h_idx, _ = pointops.knn_packed(k2, x, qq, o, no)             # same grid, other k: one launch
+    assert L.launch_count() - launches == 1
+    kk = min(k, k2)
+    assert torch.equal(h_idx[:, :kk], b_idx[:, :kk]) or name.startswith(("duplicated", "all_points"))
+    if ref_cuda.available():
+        r_idx, r_d2 = ref_cuda.knnquery(k, x, qq, o, no)
+        assert torch.equal(g_d2.view(torch.int32), r_d2.view(torch.int32)) and torch.equal(g_idx, r_idx)
+    x.add_(0.0)                                                   # in-place write bumps the version: caches must miss
+    launches = L.launch_count()
+    pointops.knn_packed(k, x, qq if qbuild is not None else x, o, no)
+    assert L.launch_count() - launches == 5
+
+
 def test_knn_full_size_property():
     """24k x 24k, k=36: row 0 is the query itself at distance 0 and rows are sorted."""
     xyz = clouds.dental_arch(24000, 1)[0].cuda()

@@ -182,6 +182,10 @@ def test_group_all_wide_vs_reference_module(train_bn):
 @pytest.mark.parametrize("train_bn", [True, False])
 @pytest.mark.parametrize("shape", [(24000, 1024, 6, 128, [64, 32]), (512, 256, 512, 1024, [1024, 1024]), (1024, 1, 64, 128, [64])])
 def test_feature_propagation_vs_reference_module(train_bn, shape):
+    """Against the reference module on the GPU and against the same module evaluated in float64 (the exact answer):
+    within 1e-4 of the reference, or -- batch-statistics BatchNorm over few rows amplifies fp32 rounding, and the
+    reference's own fp32 run then sits further than 1e-4 from the exact result -- as close to the exact result as the
+    reference is (factor 2)."""
     N, S, D1, D2, mlp = shape
     B = 2
     feats = arch(B, N)
@@ -200,10 +204,65 @@ def test_feature_propagation_vs_reference_module(train_bn, shape):
     ours = pn2.PointNetFeaturePropagation(D1 + D2, mlp).cuda().train(train_bn)
     with world("reference"), torch.no_grad():
         ref = _copy(ours, refpn().PointNetFeaturePropagation(D1 + D2, mlp).cuda()).train(train_bn)
+        state = {k: v.clone() for k, v in ref.state_dict().items()}
         want = ref(xyz1, xyz2, p1, p2)
+        ref.load_state_dict(state)
+        truth = ref.double()(xyz1.double(), xyz2.double(), p1.double(), p2.double())
     with torch.no_grad():
         got = ours(xyz1, xyz2, p1, p2)
-    assert elementwise(got, want) < REL_TOL
+    err, err_ours_t, err_ref_t = elementwise(got, want), elementwise(got, truth), elementwise(want, truth)
+    assert err < REL_TOL or err_ours_t <= max(REL_TOL, 2.0 * err_ref_t), (err, err_ours_t, err_ref_t)
+
+
+# ------------------------------------------------------------------------------------ the reference's own blocks.py on both operator sets
+def test_real_blocks_transition_down_transformer_layer_transition_up():
+    """``models/modules/cbl_point_transformer/blocks.py`` as shipped (TransitionDown :47-79, PointTransformerLayer :14-44,
+    TransitionUp :82-111), imported once per operator set; same weights, training-mode BatchNorm, forward + backward."""
+    name = "models.modules.cbl_point_transformer.blocks"
+    xyz, _, _ = clouds.dental_arch(24000, 2)
+    p = xyz.cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(24000, 32, device="cuda", generator=g)
+    o = torch.tensor([24000], dtype=torch.int32, device="cuda")
+    outs, grads, state = {}, {}, None
+    for ops in ("reference", "b200"):
+        w = world(ops)
+        with w:
+            B = w.mod(name)
+            torch.manual_seed(0)
+            mods = torch.nn.ModuleDict({"td": B.TransitionDown(32, 64, 4, 24), "pt": B.PointTransformerLayer(64, 64, 8, 24),
+                                        "tu": B.TransitionUp(64, 32), "lin": torch.nn.Linear(32, 32)}).cuda()
+            if state is None:
+                state = {k: v.clone() for k, v in mods.state_dict().items()}
+            else:
+                mods.load_state_dict(state)
+            xin = x.clone().requires_grad_(True)
+            p2, x2, o2 = mods["td"]([p, xin, o])
+            x3 = mods["pt"]([p2, x2, o2])
+            up = mods["tu"]([p, mods["lin"](xin), o], [p2, x3, o2])
+            up.square().mean().backward()
+            outs[ops] = {"p2": p2, "x2": x2, "o2": o2, "x3": x3, "up": up}
+            grads[ops] = {"x": xin.grad.clone(), **{n: q.grad.clone() for n, q in mods.named_parameters() if q.grad is not None}}
+    a, b = outs["b200"], outs["reference"]
+    assert torch.equal(a["p2"], b["p2"]) and torch.equal(a["o2"], b["o2"])          # FPS indices identical
+    for k in ("x2", "x3", "up"):
+        assert elementwise(a[k], b[k]) < REL_TOL, k
+    # backward: the gathers' scatter-adds follow torch's index_put order (csrc/csr.cu), everything else is the reference's
+    # own torch code on bit-identical inputs -> every gradient bit-identical
+    for k in ("x2", "x3", "up"):
+        assert torch.equal(a[k], b[k]), k
+    for k, want in grads["reference"].items():
+        got = grads["b200"][k]
+        assert torch.equal(got, want), (k, float((got - want).abs().max()), float(want.abs().max()))
+
+
+def test_farthest_point_sample_np_wrapper():
+    """pointnet2_utils.farthest_point_sample_np (:103-118; unused by the reference, random start there): numpy in/out,
+    deterministic start, same samples as the tensor API."""
+    xyz = clouds.dental_arch(6000, 3)[0]
+    got = pn2.farthest_point_sample_np(xyz.numpy()[None], 256)
+    want = pn2.farthest_point_sample(xyz[None].cuda(), 256).cpu().numpy()
+    assert got.dtype == np.int64 and np.array_equal(got, want)
 
 
 # ------------------------------------------------------------------------------------ whole models (C2-model, C3, C4)

@@ -21,6 +21,12 @@ _vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 _SIGS = {
     "tgn_furthestsampling": [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tgn_knnquery": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tgn_crop_knn": [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "tgn_csr_build": [ctypes.c_longlong, _i, _vp, _vp, _vp],
+    "tgn_gather_backward_det": [ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp],
+    "tgn_weighted_gather_backward_det": [ctypes.c_longlong, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "tgn_knn_grid_build": [_i, _i, _vp, _vp, _vp, _vp],
+    "tgn_knn_grid_query": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tgn_grouping_forward": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "tgn_grouping_backward": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "tgn_interpolation_forward": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
@@ -82,7 +88,7 @@ REFERENCE_LAUNCHERS = [
     "subtraction_forward_cuda_launcher", "subtraction_backward_cuda_launcher",
     "aggregation_forward_cuda_launcher", "aggregation_backward_cuda_launcher",
 ]
-EXPORTS = list(_SIGS) + REFERENCE_LAUNCHERS + ["tgn_version", "tgn_last_error", "tgn_launch_count", "tgn_pw_packed_bytes", "tgn_pw_struct_size"]
+EXPORTS = list(_SIGS) + REFERENCE_LAUNCHERS + ["tgn_version", "tgn_last_error", "tgn_launch_count", "tgn_pw_packed_bytes", "tgn_pw_struct_size", "tgn_knn_grid_bytes", "tgn_csr_bytes"]
 
 
 class TgnError(RuntimeError):
@@ -108,6 +114,10 @@ def load() -> ctypes.CDLL:
     lib.tgn_launch_count.restype = _i
     lib.tgn_pw_packed_bytes.argtypes = [_i, _i]
     lib.tgn_pw_packed_bytes.restype = ctypes.c_size_t
+    lib.tgn_csr_bytes.argtypes = [ctypes.c_longlong, _i]
+    lib.tgn_csr_bytes.restype = ctypes.c_size_t
+    lib.tgn_knn_grid_bytes.argtypes = [_i, _i]
+    lib.tgn_knn_grid_bytes.restype = ctypes.c_size_t
     lib.tgn_pw_struct_size.argtypes = [_i]
     lib.tgn_pw_struct_size.restype = _i
     if lib.tgn_pw_struct_size(0) != ctypes.sizeof(PwLayer) or lib.tgn_pw_struct_size(1) != ctypes.sizeof(PwApply):

@@ -104,9 +104,7 @@ class _GatherRows(Function):
         B, N, C = ctx.shape
         M = idx.shape[1]
         flat = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N).view(B, 1)).contiguous()
-        gi = torch.zeros((B * N, C), dtype=torch.float32, device=g.device)
-        g = g.contiguous()
-        L.call("tgn_grouping_backward", B * M, 1, C, L.ptr(g), L.ptr(flat), L.ptr(gi), L.stream_ptr())
+        gi = pointops.gather_backward(g.contiguous().view(B * M, C), flat, B * N)     # torch's index_put order (deterministic)
         return gi.view(B, N, C), None
 
 
@@ -292,7 +290,8 @@ def three_interpolate(points2, dist, idx):
     rec = 1.0 / (dist + 1e-8)
     w = (rec / torch.sum(rec, dim=2, keepdim=True)).reshape(B * N, 3).contiguous()
     flat = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * S).view(B, 1, 1)).reshape(B * N, 3).contiguous()
-    return pointops._WeightedGather.apply(p2.reshape(B * S, C), flat, w).view(B, N, C)
+    # unfused products then (a0 + a1) + a2: torch.sum(index_points(points2, idx) * weight, dim=2) (:340)
+    return pointops._WeightedGather.apply(p2.reshape(B * S, C), flat, w, "sum").view(B, N, C)
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):

@@ -75,18 +75,109 @@ class FurthestSampling(Function):
 furthestsampling = FurthestSampling.apply
 
 
+KNN_GRID_MIN_POINTS = 2048      # below this a brute-force scan of the segment is as fast as building a grid
+_knn_grid_enabled = True
+
+
+def set_knn_grid(flag: bool) -> None:
+    """Experiments / tests: False keeps every kNN on the brute-force warp kernel (csrc/knn.cu)."""
+    global _knn_grid_enabled
+    _knn_grid_enabled = bool(flag)
+
+
+class _Lru:
+    """Tiny LRU keyed by tensor identity: an entry keeps its key tensors alive, so a (data_ptr, _version) pair cannot be
+    recycled for different contents while the entry exists; an in-place change bumps ``_version`` and misses."""
+
+    def __init__(self, size: int):
+        self.size, self.items = size, []
+
+    @staticmethod
+    def sig(*tensors) -> tuple:
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+
+    def get(self, key):
+        for i, (k, _, val) in enumerate(self.items):
+            if k == key:
+                self.items.append(self.items.pop(i))
+                return val
+        return None
+
+    def put(self, key, keep_alive, val) -> None:
+        self.items.append((key, keep_alive, val))
+        if len(self.items) > self.size:
+            self.items.pop(0)
+
+    def clear(self) -> None:
+        self.items.clear()
+
+
+_grid_cache = _Lru(8)       # (xyz, offset) -> grid workspace
+_knn_cache = _Lru(16)       # (xyz, new_xyz, offset, new_offset, k) -> (idx, d2): a PointTransformerLayer asks twice (blocks.py:34-35)
+
+
+def clear_knn_caches() -> None:
+    _grid_cache.clear()
+    _knn_cache.clear()
+
+
+def _grid_for(xyz: torch.Tensor, offset: torch.Tensor) -> torch.Tensor:
+    key = _Lru.sig(xyz, offset)
+    cur = torch.cuda.current_stream()
+    hit = _grid_cache.get(key)
+    if hit is not None:
+        ws, ev, stream = hit
+        if stream != cur:                      # built on another stream: order this consumer after the build
+            cur.wait_event(ev)
+            ws.record_stream(cur)
+        return ws
+    b, n = int(offset.shape[0]), int(xyz.shape[0])
+    ws = torch.empty(L.load().tgn_knn_grid_bytes(b, n), dtype=torch.uint8, device=xyz.device)
+    L.call("tgn_knn_grid_build", b, n, L.ptr(xyz), L.ptr(offset), L.ptr(ws), L.stream_ptr())
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    _grid_cache.put(key, (xyz, offset), (ws, ev, cur))
+    return ws
+
+
 def knn_packed(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor, offset: torch.Tensor,
                new_offset: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """idx (m,nsample) int32 and SQUARED distances (m,nsample)."""
+    """idx (m,nsample) int32 and SQUARED distances (m,nsample).  Point sets of >= KNN_GRID_MIN_POINTS rows are searched
+    through a uniform grid that is built once per (xyz, offset) and cached; identical repeated queries (the two
+    ``queryandgroup`` calls of a transformer layer, every layer of a level) return the cached answer.  The cached
+    tensors are shared: treat them as read-only (an in-place write invalidates the entry)."""
     _need(xyz, torch.float32, "xyz")
     _need(new_xyz, torch.float32, "new_xyz")
     _need(offset, torch.int32, "offset")
     _need(new_offset, torch.int32, "new_offset")
     m = new_xyz.shape[0]
+    n, b = int(xyz.shape[0]), int(offset.shape[0])
+    use_grid = _knn_grid_enabled and n >= KNN_GRID_MIN_POINTS and b <= 4096
+    key = None
+    if use_grid:
+        key = _Lru.sig(xyz, new_xyz, offset, new_offset) + (int(nsample),)
+        hit = _knn_cache.get(key)
+        if hit is not None:
+            idx, d2, versions, ev, stream = hit
+            if (idx._version, d2._version) == versions:
+                cur = torch.cuda.current_stream()
+                if stream != cur:
+                    cur.wait_event(ev)
+                    idx.record_stream(cur)
+                    d2.record_stream(cur)
+                return idx, d2
     idx = _empty((m, nsample), torch.int32, xyz)
     d2 = _empty((m, nsample), torch.float32, xyz)
-    L.call("tgn_knnquery", int(offset.shape[0]), int(m), int(nsample), L.ptr(xyz), L.ptr(new_xyz), L.ptr(offset),
-           L.ptr(new_offset), L.ptr(idx), L.ptr(d2), L.stream_ptr())
+    if use_grid:
+        ws = _grid_for(xyz, offset)
+        L.call("tgn_knn_grid_query", b, n, int(m), int(nsample), L.ptr(xyz), L.ptr(new_xyz), L.ptr(offset), L.ptr(new_offset),
+               L.ptr(ws), L.ptr(idx), L.ptr(d2), L.stream_ptr())
+        ev = torch.cuda.Event()
+        ev.record()
+        _knn_cache.put(key, (xyz, new_xyz, offset, new_offset), (idx, d2, (idx._version, d2._version), ev, torch.cuda.current_stream()))
+    else:
+        L.call("tgn_knnquery", b, int(m), int(nsample), L.ptr(xyz), L.ptr(new_xyz), L.ptr(offset),
+               L.ptr(new_offset), L.ptr(idx), L.ptr(d2), L.stream_ptr())
     return idx, d2
 
 
@@ -98,12 +189,60 @@ class KNNQuery(Function):
         if new_xyz is None:
             new_xyz = xyz
         idx, d2 = knn_packed(int(nsample), xyz, new_xyz, offset, new_offset)
+        idx = idx.view_as(idx)              # a fresh tensor object over the (possibly cached, shared) storage
         dist = torch.sqrt(d2)
         ctx.mark_non_differentiable(idx, dist)
         return idx, dist
 
 
 knnquery = KNNQuery.apply
+
+
+_deterministic_backward = True
+_csr_cache = _Lru(16)       # index tensor -> inverse index (CSR)
+
+
+def set_deterministic_backward(flag: bool) -> None:
+    """True (default): the scatter-add backwards of grouping / index_points / pointops.interpolation add each
+    destination row's contributions in ascending source position through an inverse index -- torch's index_put
+    order, i.e. gradients bit-identical to the reference's autograd and reproducible.  False: fp32 atomics."""
+    global _deterministic_backward
+    _deterministic_backward = bool(flag)
+
+
+def csr_for(keys: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """Inverse index of a flat int32 key tensor (cached per tensor identity; the kNN cache hands the same ``idx`` to
+    every layer of a level, so one build serves all their backwards)."""
+    key = _Lru.sig(keys) + (int(n_rows),)
+    cur = torch.cuda.current_stream()
+    hit = _csr_cache.get(key)
+    if hit is not None:
+        ws, ev, stream = hit
+        if stream != cur:
+            cur.wait_event(ev)
+            ws.record_stream(cur)
+        return ws
+    M = keys.numel()
+    ws = torch.empty(L.load().tgn_csr_bytes(M, int(n_rows)), dtype=torch.uint8, device=keys.device)
+    L.call("tgn_csr_build", M, int(n_rows), L.ptr(keys), L.ptr(ws), L.stream_ptr())
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    _csr_cache.put(key, (keys,), (ws, ev, cur))
+    return ws
+
+
+def gather_backward(grad_output: torch.Tensor, idx: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """grad wrt ``input`` of ``input[idx]``: grad_output (..., c) with idx.numel() leading rows -> (n_rows, c)."""
+    c = grad_output.shape[-1]
+    M = idx.numel()
+    if _deterministic_backward:
+        ws = csr_for(idx, n_rows)
+        grad_in = torch.empty((n_rows, c), dtype=torch.float32, device=grad_output.device)
+        L.call("tgn_gather_backward_det", M, int(n_rows), int(c), L.ptr(ws), L.ptr(grad_output), L.ptr(grad_in), L.stream_ptr())
+        return grad_in
+    grad_in = torch.zeros((n_rows, c), dtype=torch.float32, device=grad_output.device)
+    L.call("tgn_grouping_backward", M, 1, c, L.ptr(grad_output), L.ptr(idx), L.ptr(grad_in), L.stream_ptr())
+    return grad_in
 
 
 class Grouping(Function):
@@ -124,11 +263,7 @@ class Grouping(Function):
     @staticmethod
     def backward(ctx, grad_output):
         (idx,) = ctx.saved_tensors
-        grad_output = grad_output.contiguous()
-        m, nsample, c = grad_output.shape
-        grad_in = torch.zeros((ctx.n, c), dtype=torch.float32, device=grad_output.device)
-        L.call("tgn_grouping_backward", m, nsample, c, L.ptr(grad_output), L.ptr(idx), L.ptr(grad_in), L.stream_ptr())
-        return grad_in, None
+        return gather_backward(grad_output.contiguous(), idx, ctx.n), None
 
 
 grouping = Grouping.apply
@@ -225,14 +360,17 @@ class _WeightedGather(Function):
 
     @staticmethod
     def forward(ctx, input, idx, weight, fused=True):
+        """``fused``: True = the FMA chain of the reference KERNEL (interpolation_cuda_kernel.cu), atomics backward like it;
+        False = pointops.interpolation's torch loop (unfused, k index_put backwards); "sum" = pointnet2's
+        torch.sum(index_points(.) * weight, dim=2) (unfused forward, ONE index_put backward)."""
         _need(input, torch.float32, "input")
         _need(idx, torch.int32, "idx")
         _need(weight, torch.float32, "weight")
         n, k = idx.shape
         m, c = input.shape
         out = torch.zeros((n, c), dtype=torch.float32, device=input.device)
-        L.call("tgn_weighted_gather", n, c, k, L.ptr(input), L.ptr(idx), L.ptr(weight), L.ptr(out), 1 if fused else 0, L.stream_ptr())
-        ctx.m = m
+        L.call("tgn_weighted_gather", n, c, k, L.ptr(input), L.ptr(idx), L.ptr(weight), L.ptr(out), 1 if fused is True else 0, L.stream_ptr())
+        ctx.m, ctx.fused = m, fused
         ctx.save_for_backward(idx, weight)
         return out
 
@@ -241,8 +379,16 @@ class _WeightedGather(Function):
         idx, weight = ctx.saved_tensors
         grad_output = grad_output.contiguous()
         n, c = grad_output.shape
+        k = idx.shape[1]
+        if _deterministic_backward and ctx.fused is not True and k <= 8:
+            # the torch-loop form (pointops.interpolation): k index_put accumulations summed by autograd, reproduced exactly
+            ws = csr_for(idx, ctx.m)
+            gi = torch.empty((ctx.m, c), dtype=torch.float32, device=grad_output.device)
+            L.call("tgn_weighted_gather_backward_det", idx.numel(), int(ctx.m), int(c), int(k), 1 if ctx.fused == "sum" else 0,
+                   L.ptr(ws), L.ptr(grad_output), L.ptr(weight), L.ptr(gi), L.stream_ptr())
+            return gi, None, None, None
         gi = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad_output.device)
-        L.call("tgn_interpolation_backward", n, c, idx.shape[1], L.ptr(grad_output), L.ptr(idx), L.ptr(weight), L.ptr(gi), L.stream_ptr())
+        L.call("tgn_interpolation_backward", n, c, k, L.ptr(grad_output), L.ptr(idx), L.ptr(weight), L.ptr(gi), L.stream_ptr())
         return gi, None, None, None
 
 
