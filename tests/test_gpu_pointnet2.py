@@ -177,36 +177,31 @@ def test_feature_propagation_matches_reference_fixture(golden_dir, mode):
     assert rel_err(out.cpu().numpy(), fix[f"out_{mode}"]) < REL_TOL
 
 
-def test_feature_propagation_backward_matches_autograd_of_dense_form():
-    """Gradient wrt the coarse features through the CUDA interpolate backward == autograd through
-    the reference's dense formulation."""
+def test_interpolation_forward_backward_bitwise_vs_dense_torch_form():
+    """3-NN + inverse-distance interpolation through the CUDA kernels (three_nn, weighted gather with the order-exact
+    backward) == the reference's dense formulation (:333-340: square_distance, sort, reciprocal, normalise, weighted sum)
+    evaluated by torch on the GPU -- forward values and the gradient wrt the coarse features, bit for bit, including
+    fine points that coincide with a coarse one (expanded-form distances of -6e-8 there)."""
+    pn2.set_reference_device("cuda")     # the dense form below IS torch on the GPU
     g = torch.Generator().manual_seed(0)
     x1 = clouds.dental_arch(1500, 1)[0].cuda()
     x2 = x1[:200].contiguous()
     p2 = torch.randn(1, 12, 200, generator=g).cuda().requires_grad_(True)
-    pn2.set_reference_device("cuda")     # the dense form below IS torch on the GPU
-    fp = pn2.PointNetFeaturePropagation(12, [8]).cuda().eval()      # running statistics: no batch-statistics amplification in a backward test
     c1, c2 = x1.t()[None].contiguous(), x2.t()[None].contiguous()
-    out = fp(c1, c2, None, p2)
-    out.square().sum().backward()
-    got = p2.grad.clone()
-    p2.grad = None
-    d = pn2.square_distance(c1.permute(0, 2, 1), c2.permute(0, 2, 1))     # the same strided views the module's square_distance would see
-    dd, ii = d.sort(dim=-1)
+    v1, v2 = c1.permute(0, 2, 1), c2.permute(0, 2, 1)                    # the strided views the module's square_distance sees
+    dist, idx = pn2.three_nn(pn2._to_point_major(c1), pn2._to_point_major(c2), pn2._alt(v1) | (pn2._alt(v2) << 1))
+    dd, ii = pn2.square_distance(v1, v2).sort(dim=-1)
+    assert torch.equal(dist, dd[:, :, :3]) and torch.equal(idx.long(), ii[:, :, :3])
+    interp = pn2.three_interpolate(pn2._transpose(p2), dist, idx)        # autograd path
     rec = 1.0 / (dd[:, :, :3] + 1e-8)
     w = rec / rec.sum(2, keepdim=True)
-    pts = p2.permute(0, 2, 1)
-    interp = (pts[0][ii[0, :, :3]] * w[0].unsqueeze(-1)).sum(1)[None]
-    h = interp.permute(0, 2, 1)
-    saved = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False          # the module runs its library convolutions in IEEE fp32; so must the dense form
-    try:
-        for conv, bn in zip(fp.mlp_convs, fp.mlp_bns):
-            h = torch.relu(bn(conv(h)))
-        h.square().sum().backward()
-    finally:
-        torch.backends.cudnn.allow_tf32 = saved
-    assert rel_err(got.cpu().numpy(), p2.grad.cpu().numpy()) < REL_TOL
+    dense = (p2.permute(0, 2, 1)[0][ii[0, :, :3]] * w[0].unsqueeze(-1)).sum(1)[None]
+    assert torch.equal(interp, dense)
+    assert torch.equal(pn2.three_interpolate(pn2._transpose(p2).detach(), dist, idx), dense)      # fused no-grad kernel
+    go = torch.randn(interp.shape, generator=g).cuda()
+    (ga,) = torch.autograd.grad(interp, p2, go)
+    (gb,) = torch.autograd.grad(dense, p2, go)
+    assert torch.equal(ga, gb)
 
 
 # ------------------------------------------------------------------------------------ set abstraction

@@ -214,6 +214,40 @@ def test_feature_propagation_vs_reference_module(train_bn, shape):
     assert err < REL_TOL or err_ours_t <= max(REL_TOL, 2.0 * err_ref_t), (err, err_ours_t, err_ref_t)
 
 
+def test_feature_propagation_forward_backward_under_autograd_bitwise():
+    """Training step through PointNetFeaturePropagation (autograd on): 3-NN, interpolation (CUDA gather with the order-exact
+    backward) and the reference's own conv/BN torch code -> output and every gradient bit-identical to the reference module."""
+    N, S, D1, D2, mlp = 6000, 512, 6, 64, [32, 16]
+    feats = arch(2, N)
+    xyz1 = feats[:, :3, :]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    with world("reference"):
+        x1v = xyz1.permute(0, 2, 1)
+        xyz2 = refpn().index_points(x1v, refpn().farthest_point_sample(x1v, S)).permute(0, 2, 1)
+    p1 = torch.randn(2, D1, N, device="cuda", generator=g)
+    p2 = torch.randn(2, D2, S, device="cuda", generator=g)
+    torch.manual_seed(0)
+    ours = pn2.PointNetFeaturePropagation(D1 + D2, mlp).cuda().train()
+    res = {}
+    for name in ("reference", "b200"):
+        a1, a2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+        if name == "reference":
+            with world("reference"):
+                mod = _copy(ours, refpn().PointNetFeaturePropagation(D1 + D2, mlp).cuda()).train()
+                out = mod(xyz1, xyz2, a1, a2)
+        else:
+            mod = ours
+            out = mod(xyz1, xyz2, a1, a2)
+        out.square().mean().backward()
+        res[name] = {"out": out.detach(), "g_p1": a1.grad, "g_p2": a2.grad, **{n: q.grad for n, q in mod.named_parameters()}}
+    for k, want in res["reference"].items():
+        got = res["b200"][k]
+        if k in ("out", "g_p1", "g_p2"):
+            assert torch.equal(got, want), (k, float((got - want).abs().max()))
+        else:       # cuDNN's weight-gradient kernels are not bit-reproducible run to run; the inputs to them are identical
+            assert elementwise(got, want) < 1e-5, k
+
+
 # ------------------------------------------------------------------------------------ the reference's own blocks.py on both operator sets
 def test_real_blocks_transition_down_transformer_layer_transition_up():
     """``models/modules/cbl_point_transformer/blocks.py`` as shipped (TransitionDown :47-79, PointTransformerLayer :14-44,

@@ -29,10 +29,11 @@ class HostPipeline:
     kernel efficiency ((2,3,2,1): 5.5e7, (2,5,1): 4.6e7), so that is the default."""
 
     def __init__(self, module: torch.nn.Module, chunk_clouds: int = 148, n_streams: int = 2,
-                 groups: Sequence[int] = (1,)):
+                 groups: Sequence[int] = (1,), fps_mode: int = None):
         self.module = module
         self.chunk = int(chunk_clouds)
         self.groups = tuple(int(g) for g in groups) or (1,)
+        self.fps_mode = fps_mode          # None: shape by the clouds in flight; else the tgn_furthestsampling mode of every chunk
         self.streams: List[torch.cuda.Stream] = [torch.cuda.Stream() for _ in range(max(1, int(n_streams)))]
         self.copy_in = torch.cuda.Stream()
         self.copy_out = torch.cuda.Stream()
@@ -79,7 +80,8 @@ class HostPipeline:
             s = self.streams[gi % len(self.streams)]
             s.wait_event(landed[k1])
             # FPS shape for the clouds resident on the GPU (this group and its neighbour on the other stream)
-            pn2.set_fps_mode(pn2.fps_mode_for_clouds_in_flight(min(B, (hi - lo) * len(self.streams)), host_feats.shape[2]))
+            pn2.set_fps_mode(self.fps_mode if self.fps_mode is not None else
+                             pn2.fps_mode_for_clouds_in_flight(min(B, (hi - lo) * len(self.streams)), host_feats.shape[2]))
             with torch.cuda.stream(s):
                 d = dev[lo:hi]
                 new_xyz, new_points = self.module(d[:, :3].contiguous(), d)
