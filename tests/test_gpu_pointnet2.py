@@ -306,6 +306,11 @@ SA_SHAPES = [
     # (N, S, r, K, D, widths, engine)        BASELINE C2(i) at full size first
     (24000, 1024, 0.1, 32, 6, [32, 32, 64], pn2.ENGINE_TC),
     (24000, 1024, 0.1, 32, 6, [32, 32, 64], pn2.ENGINE_FP32),
+    (24000, 1024, 0.1, 32, 6, [32, 32, 64], pn2.ENGINE_TC8),      # eight tile groups per SM, bf16x3 operands
+    (4096, 1024, 0.1, 16, 6, [32, 32, 64], pn2.ENGINE_TC8),       # two neighbourhoods per warp
+    (6000, 1001, 0.1, 32, 6, [32, 32, 64], pn2.ENGINE_TC8),       # S not a multiple of 4: partial tile, scalar output path
+    (3000, 300, 0.15, 16, 0, [16], pn2.ENGINE_TC8),               # xyz only, single layer
+    (5000, 512, 0.1, 32, 13, [20, 40, 24, 60], pn2.ENGINE_TC8),   # four layers, odd widths, full 16-channel input
     (4096, 1024, 0.1, 16, 6, [32, 32, 64], pn2.ENGINE_TC),
     (16384, 700, 0.1, 64, 6, [32, 32, 64], pn2.ENGINE_TC),
     (3000, 200, 0.15, 24, 6, [20, 40], pn2.ENGINE_TC),          # K that does not divide 128, odd widths

@@ -255,6 +255,12 @@ extern "C" int tgn_sa_group_mlp_max(int B, int N, int S, int K, int D, const flo
     // auto: the 3xTF32 tensor-core engine when the shape fits it (widths <= 64), else the wide tensor-core
     // engine (tf32 first layer, bf16x2-split later layers: ~1e-5 relative, inside the 1e-4 bar), else the
     // exact-FMA CUDA-core engine (any K, widths <= 128)
+    // engine 4: eight tile groups per SM, bf16x3 operands (C_in <= 16, widths <= 64, K in {16, 32}); on request only until
+    // its measured time beats engine 2 on the bench shape (profiles/)
+    if (engine == 4) {
+        if (!sa_mlp_tc8_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the eight-group tcgen05 engine"); return TGN_ERR_INVALID; }
+        return sa_mlp_tc8_launch(p, st);
+    }
     if (engine == 2 || (engine == 0 && sa_mlp_tc_supported(p))) {
         if (!sa_mlp_tc_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
         return sa_mlp_tc_launch(p, st);

@@ -35,7 +35,7 @@ from . import pointops
 
 SA_FUSED_MAX_WIDTH = 128
 SA_FUSED_MAX_LAYERS = 4
-ENGINE_AUTO, ENGINE_FP32, ENGINE_TC, ENGINE_TCW = 0, 1, 2, 3     # TCW: wide layers, tf32 first layer + bf16x2-split later layers
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TC, ENGINE_TCW, ENGINE_TC8 = 0, 1, 2, 3, 4     # TCW: wide layers (bf16x2); TC8: eight tile groups, bf16x3
 _sa_engine = ENGINE_AUTO
 
 
