@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=148, help="clouds per pipelined chunk of the end-to-end measurement")
     ap.add_argument("--e2e-streams", type=int, default=2)
     ap.add_argument("--e2e-groups", default="1", help="chunks per compute group of the end-to-end pipeline")
+    ap.add_argument("--e2e-sa-engine", type=int, default=None, help="group-MLP engine inside the end-to-end pipeline (5: half-size CTAs that co-reside with other chunks' kernels)")
     ap.add_argument("--e2e-fps-mode", type=int, default=None, help="FPS shape of every pipelined chunk (-14: 4 warps per cloud, -18: 8, -26: 16); default: by clouds in flight")
     ap.add_argument("--fps-mode", type=int, default=0, help="0 auto; 100*G+CS resident shape, -2 bucket, -(10+W) bucket with W warps per cloud (experiments)")
     ap.add_argument("--ball-path", type=int, default=0, help="0 auto, 4 index-order tile scan, 8 uniform grid (experiments)")
@@ -368,7 +369,7 @@ def main():
 
     from toothgroupnetwork_b200.pipeline import HostPipeline
     pipe = HostPipeline(sa, chunk_clouds=args.e2e_chunk, n_streams=args.e2e_streams,
-                        groups=[int(g) for g in args.e2e_groups.split(",")], fps_mode=args.e2e_fps_mode)
+                        groups=[int(g) for g in args.e2e_groups.split(",")], fps_mode=args.e2e_fps_mode, sa_engine=args.e2e_sa_engine)
 
     def e2e_step():
         # public API on host buffers: chunks of the batch go H2D -> module.forward -> D2H on a few

@@ -436,6 +436,16 @@ int fps_dispatch(int b, int n_max, const float* xyz, const int* offset, const in
     // Auto: small clouds stay register-resident in one CTA (cheapest iteration); everything larger
     // goes to the bucket-pruned kernel, which wins both on latency and on throughput.
     // mode -2: bucket kernel, shape by batch size; mode -(10 + W): bucket kernel with W warps per cloud.
+    // mode -3 / -(40 + W): the same with the single-barrier schedule (fps_bucket_kernel2).
+    if (mode == -3 || (mode <= -41 && mode >= -72)) {
+        if (n_max > fps_bucket_max_points()) { set_error("furthestsampling: n_max=%d exceeds the bucket kernel", n_max); return TGN_ERR_INVALID; }
+        return fps_bucket_launch(b, n_max, xyz, offset, new_offset, tmp, idx, bs_log2, 100 + (mode == -3 ? 0 : -mode - 40), stream);
+    }
+    // mode -(80 + W): single barrier AND register-resident bucket tables (fps_bucket_kernel3; clouds of up to 4 buckets per lane).
+    if (mode <= -81 && mode >= -112) {
+        if (n_max > fps_bucket_max_points()) { set_error("furthestsampling: n_max=%d exceeds the bucket kernel", n_max); return TGN_ERR_INVALID; }
+        return fps_bucket_launch(b, n_max, xyz, offset, new_offset, tmp, idx, bs_log2, 200 + (-mode - 80), stream);
+    }
     if (mode == -2 || (mode <= -11 && mode >= -26) || (mode == 0 && n_max > 4096 && n_max <= fps_bucket_max_points())) {
         if (n_max > fps_bucket_max_points()) { set_error("furthestsampling: n_max=%d exceeds the bucket kernel", n_max); return TGN_ERR_INVALID; }
         return fps_bucket_launch(b, n_max, xyz, offset, new_offset, tmp, idx, bs_log2, mode <= -11 ? -mode - 10 : 0, stream);

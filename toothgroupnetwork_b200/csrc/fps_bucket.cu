@@ -529,6 +529,323 @@ fps_bucket_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     }
 }
 
+// ---- single-barrier main kernel ("v2") ------------------------------------------------------------------------------------
+// Same tables, same exact update, same candidates -- a different schedule.  The kernel above spends an iteration on three
+// block barriers (owner warps collect the active buckets | all warps process them | owners refresh | arg-max) around one
+// memory round trip.  Here bucket bk belongs to warp bk mod W for good (the buckets are Morton-sorted, so the ~10 buckets a
+// new sample touches are consecutive and land on ~10 different warps), and a warp does everything for its own buckets
+// back to back: box tests (one bucket per lane per pass), exact update of its active buckets (two in flight), refresh of
+// its best candidate -- then publishes (value, key, x, y, z) in a double-buffered slot and meets the others at ONE barrier,
+// after which every warp reduces the W slots to the next sample.  The winner's coordinates travel in the slot, so nobody
+// reads a bucket table entry that a faster warp may already be overwriting for the next iteration.
+template <int MT_>
+__global__ void __launch_bounds__(MT_, 1024 / MT_)
+fps_bucket_kernel2(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
+                   float* tmp, int* __restrict__ idx, BucketWs ws, int bs_log2)
+{
+    constexpr int kMT = MT_, kMNW = MT_ / 32;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    struct Slot { int v, k; float x, y, z; int pad[3]; };
+    __shared__ Slot slot[2][kMNW];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const int start_n = cloud ? offset[cloud - 1] : 0;
+    const int n = offset[cloud] - start_n;
+    const int start_m = cloud ? new_offset[cloud - 1] : 0;
+    const int m = new_offset[cloud] - start_m;
+    if (m <= 0 || n <= 0) return;
+    if (tid == 0) idx[start_m] = start_n;                      // sampling_cuda_kernel.cu:39
+    if (m == 1) return;
+
+    const int nb = (n + kBP - 1) / kBP;
+    float4* blo = reinterpret_cast<float4*>(dyn);                                   // [nbmax] box min, w = skip threshold
+    float4* bhi = blo + ws.nbmax;                                                   // [nbmax] box max, w = candidate value bits
+    float4* cxyz = bhi + ws.nbmax;                                                  // [nbmax] candidate x,y,z,key bits
+
+    const float4* __restrict__ pa = ws.pa + static_cast<size_t>(cloud) * (ws.stride / 2);
+    const float4* __restrict__ pb = ws.pb + static_cast<size_t>(cloud) * (ws.stride / 2);
+    float2* tv2 = ws.tv + static_cast<size_t>(cloud) * (ws.stride / 2);
+    {
+        const float4* glo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
+        const float4* ghi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
+        const float4* gx = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
+        for (int bk = tid; bk < nb; bk += kMT) {
+            float4 lo = glo[bk];
+            lo.w = skip_threshold(lo.w);                     // w held the bucket's initial max t
+            blo[bk] = lo; bhi[bk] = ghi[bk]; cxyz[bk] = gx[bk];
+        }
+    }
+    __syncthreads();
+
+    // best candidate over this warp's buckets (warp, warp + W, ...) -> registers of every lane
+    int my_v = INT_MIN, my_k = INT_MAX;
+    float my_x = 0.f, my_y = 0.f, my_z = 0.f;
+    auto refresh_own = [&]() {
+        int bv = INT_MIN, bkey = INT_MAX, bbk = -1;
+        for (int bk = warp + kMNW * lane; bk < nb; bk += kMNW * 32) {
+            const int v = __float_as_int(bhi[bk].w), k = __float_as_int(cxyz[bk].w);
+            if (v > bv || (v == bv && k < bkey)) { bv = v; bkey = k; bbk = bk; }
+        }
+        my_v = __reduce_max_sync(FULL, bv);
+        my_k = __reduce_min_sync(FULL, bv == my_v ? bkey : INT_MAX);
+        const int src = __ffs(__ballot_sync(FULL, bv == my_v && bkey == my_k && bbk >= 0)) - 1;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0) {
+            const int wb = __shfl_sync(FULL, bbk, src);
+            w = cxyz[wb];
+        }
+        my_x = w.x; my_y = w.y; my_z = w.z;
+    };
+    refresh_own();
+
+    float ox = __ldg(xyz + 3 * static_cast<size_t>(start_n)), oy = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 1),
+          oz = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 2);
+
+    for (int it = 1; it < m; ++it) {
+        const uint64_t ox2 = pack2(ox, ox), oy2 = pack2(oy, oy), oz2 = pack2(oz, oz);
+        bool dirty = false;
+        // ---- own buckets: test 32 per pass, update the active ones (kBatch in flight) ---------------------------------
+        for (int base = warp; base < nb; base += kMNW * 32) {
+            const int bk_l = base + kMNW * lane;
+            bool act = false;
+            if (bk_l < nb) {
+                const float4 lo = blo[bk_l], hi = bhi[bk_l];
+                act = !(box_dist2(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, ox, oy, oz) > lo.w);
+            }
+            unsigned mask = __ballot_sync(FULL, act);
+            dirty |= mask != 0u;
+            while (mask) {
+                int bk[kBatch];
+                float4 A[kBatch], B[kBatch];
+                float2 T[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    if (mask) {
+                        const int l = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        bk[u] = base + kMNW * l;
+                        A[u] = __ldg(pa + bk[u] * 32 + lane);
+                        B[u] = __ldg(pb + bk[u] * 32 + lane);
+                        T[u] = __ldcg(tv2 + bk[u] * 32 + lane);
+                    } else {
+                        bk[u] = -1;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    if (bk[u] < 0) break;                         // warp-uniform
+                    const uint64_t dx = sub2(pack2(A[u].x, A[u].y), ox2), dy = sub2(pack2(A[u].z, A[u].w), oy2),
+                                   dz = sub2(pack2(B[u].x, B[u].y), oz2);
+                    uint64_t d = mul2(dy, dy);
+                    d = fma2(dx, dx, d);
+                    d = fma2(dz, dz, d);
+                    float d0, d1;
+                    unpack2(d, d0, d1);
+                    const float n0 = fminf(d0, T[u].x), n1 = fminf(d1, T[u].y);
+                    if (n0 < T[u].x || n1 < T[u].y) __stcg(tv2 + bk[u] * 32 + lane, make_float2(n0, n1));
+                    const int b0 = __float_as_int(n0), b1 = __float_as_int(n1);          // pads stay at -1
+                    const int k0 = __float_as_int(B[u].z), k1 = __float_as_int(B[u].w);
+                    const bool take1 = b1 > b0 || (b1 == b0 && k1 < k0);
+                    const int bl = take1 ? b1 : b0, kl = take1 ? k1 : k0;
+                    const int wmax = __reduce_max_sync(FULL, bl);
+                    const int wkey = __reduce_min_sync(FULL, bl == wmax ? kl : INT_MAX);
+                    if (bl == wmax && kl == wkey) {
+                        cxyz[bk[u]] = make_float4(take1 ? A[u].y : A[u].x, take1 ? A[u].w : A[u].z, take1 ? B[u].y : B[u].x,
+                                                  __int_as_float(wkey));
+                        bhi[bk[u]].w = __int_as_float(wmax);
+                        blo[bk[u]].w = skip_threshold(__int_as_float(wmax));
+                    }
+                }
+            }
+        }
+        // ---- this warp's candidate (only the warp itself writes its buckets' entries) ------------------------------------
+        if (dirty) {
+            __syncwarp();
+            refresh_own();
+        }
+        Slot* sl = slot[it & 1];
+        if (lane == 0) { sl[warp].v = my_v; sl[warp].k = my_k; sl[warp].x = my_x; sl[warp].y = my_y; sl[warp].z = my_z; }
+        __syncthreads();
+        {
+            int cv = INT_MIN, ck = INT_MAX;
+            if (lane < kMNW) { cv = sl[lane].v; ck = sl[lane].k; }
+            const int gv = __reduce_max_sync(FULL, cv);
+            const int gk = __reduce_min_sync(FULL, cv == gv ? ck : INT_MAX);
+            const int src = __ffs(__ballot_sync(FULL, cv == gv && ck == gk)) - 1;
+            ox = sl[src].x; oy = sl[src].y; oz = sl[src].z;
+            if (tid == 0) idx[start_m + it] = start_n + key_to_index(gk, bs_log2);
+        }
+    }
+
+    if (tmp) {
+        __syncthreads();
+        for (int q = tid; q < nb * 32; q += kMT) {           // q = bucket * 32 + lane
+            const float4 B = __ldg(pb + q);
+            const float2 T = __ldcg(tv2 + q);
+            const int k0 = __float_as_int(B.z), k1 = __float_as_int(B.w);
+            if (k0 != INT_MAX) tmp[start_n + key_to_index(k0, bs_log2)] = T.x;
+            if (k1 != INT_MAX) tmp[start_n + key_to_index(k1, bs_log2)] = T.y;
+        }
+    }
+}
+
+// ---- register-resident bucket tables ("v3") --------------------------------------------------------------------------------
+// At small batches (one cloud per SM or fewer) an iteration is a DEPENDENT CHAIN: ncu (profiles/r2_fps_b1_*.csv) shows ~190
+// warp instructions per warp per iteration at ~15 cycles each, 26 % issue utilisation, most samples waiting at the barrier for
+// the warp that had a bucket to update.  v3 keeps the single barrier of v2 and shortens the chain: the table entries of a
+// warp's OWN buckets (box, skip threshold, candidate value / key / coordinates: 12 registers per bucket, BPL buckets per lane)
+// never leave registers -- box tests need no shared-memory loads, an update hands the new candidate to the owner lane with
+// three shuffles, the warp's candidate is two CREDUX over registers and the winning lane publishes its slot directly.
+template <int MT_, int BPL>
+__global__ void __launch_bounds__(MT_, 1024 / MT_ > 2 ? 2 : 1024 / MT_)
+fps_bucket_kernel3(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
+                   float* tmp, int* __restrict__ idx, BucketWs ws, int bs_log2)
+{
+    constexpr int kMT = MT_, kMNW = MT_ / 32;
+    struct Slot { int v, k; float x, y, z; int pad[3]; };
+    __shared__ Slot slot[2][kMNW];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const int start_n = cloud ? offset[cloud - 1] : 0;
+    const int n = offset[cloud] - start_n;
+    const int start_m = cloud ? new_offset[cloud - 1] : 0;
+    const int m = new_offset[cloud] - start_m;
+    if (m <= 0 || n <= 0) return;
+    if (tid == 0) idx[start_m] = start_n;                      // sampling_cuda_kernel.cu:39
+    if (m == 1) return;
+
+    const int nb = (n + kBP - 1) / kBP;
+    const float4* __restrict__ pa = ws.pa + static_cast<size_t>(cloud) * (ws.stride / 2);
+    const float4* __restrict__ pb = ws.pb + static_cast<size_t>(cloud) * (ws.stride / 2);
+    float2* tv2 = ws.tv + static_cast<size_t>(cloud) * (ws.stride / 2);
+
+    // own buckets: bucket (warp + W * (lane + 32 j)), j < BPL
+    float lx[BPL], ly[BPL], lz[BPL], hx[BPL], hy[BPL], hz[BPL], thr[BPL], cx[BPL], cy[BPL], cz[BPL];
+    int cv[BPL], ck[BPL];
+    {
+        const float4* glo = ws.box_lo + static_cast<size_t>(cloud) * ws.nbmax;
+        const float4* ghi = ws.box_hi + static_cast<size_t>(cloud) * ws.nbmax;
+        const float4* gx = ws.bxyz + static_cast<size_t>(cloud) * ws.nbmax;
+#pragma unroll
+        for (int j = 0; j < BPL; ++j) {
+            const int bk = warp + kMNW * (lane + 32 * j);
+            if (bk < nb) {
+                const float4 lo = glo[bk], hi = ghi[bk], c = gx[bk];
+                lx[j] = lo.x; ly[j] = lo.y; lz[j] = lo.z; thr[j] = skip_threshold(lo.w);
+                hx[j] = hi.x; hy[j] = hi.y; hz[j] = hi.z; cv[j] = __float_as_int(hi.w);
+                cx[j] = c.x; cy[j] = c.y; cz[j] = c.z; ck[j] = __float_as_int(c.w);
+            } else {
+                lx[j] = ly[j] = lz[j] = INFINITY; hx[j] = hy[j] = hz[j] = -INFINITY; thr[j] = -1.f;     // never active
+                cv[j] = INT_MIN; ck[j] = INT_MAX; cx[j] = cy[j] = cz[j] = 0.f;
+            }
+        }
+    }
+    float ox = __ldg(xyz + 3 * static_cast<size_t>(start_n)), oy = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 1),
+          oz = __ldg(xyz + 3 * static_cast<size_t>(start_n) + 2);
+
+    for (int it = 1; it < m; ++it) {
+        const uint64_t ox2 = pack2(ox, ox), oy2 = pack2(oy, oy), oz2 = pack2(oz, oz);
+#pragma unroll
+        for (int j = 0; j < BPL; ++j) {
+            const bool act = !(box_dist2(lx[j], ly[j], lz[j], hx[j], hy[j], hz[j], ox, oy, oz) > thr[j]);
+            unsigned mask = __ballot_sync(FULL, act);
+            while (mask) {
+                int ol[kBatch];                               // owner lanes of the buckets in flight
+                float4 A[kBatch], B[kBatch];
+                float2 T[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    if (mask) {
+                        ol[u] = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int bk = warp + kMNW * (ol[u] + 32 * j);
+                        A[u] = __ldg(pa + bk * 32 + lane);
+                        B[u] = __ldg(pb + bk * 32 + lane);
+                        T[u] = __ldcg(tv2 + bk * 32 + lane);
+                    } else {
+                        ol[u] = -1;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    if (ol[u] < 0) break;                         // warp-uniform
+                    const int bk = warp + kMNW * (ol[u] + 32 * j);
+                    const uint64_t dx = sub2(pack2(A[u].x, A[u].y), ox2), dy = sub2(pack2(A[u].z, A[u].w), oy2),
+                                   dz = sub2(pack2(B[u].x, B[u].y), oz2);
+                    uint64_t d = mul2(dy, dy);
+                    d = fma2(dx, dx, d);
+                    d = fma2(dz, dz, d);
+                    float d0, d1;
+                    unpack2(d, d0, d1);
+                    const float n0 = fminf(d0, T[u].x), n1 = fminf(d1, T[u].y);
+                    if (n0 < T[u].x || n1 < T[u].y) __stcg(tv2 + bk * 32 + lane, make_float2(n0, n1));
+                    const int b0 = __float_as_int(n0), b1 = __float_as_int(n1);          // pads stay at -1
+                    const int k0 = __float_as_int(B[u].z), k1 = __float_as_int(B[u].w);
+                    const bool take1 = b1 > b0 || (b1 == b0 && k1 < k0);
+                    const int bl = take1 ? b1 : b0, kl = take1 ? k1 : k0;
+                    const int wmax = __reduce_max_sync(FULL, bl);
+                    const int wkey = __reduce_min_sync(FULL, bl == wmax ? kl : INT_MAX);
+                    const int wl = __ffs(__ballot_sync(FULL, bl == wmax && kl == wkey)) - 1;      // the lane holding the candidate point
+                    const float nx = __shfl_sync(FULL, take1 ? A[u].y : A[u].x, wl), ny = __shfl_sync(FULL, take1 ? A[u].w : A[u].z, wl),
+                                nz = __shfl_sync(FULL, take1 ? B[u].y : B[u].x, wl);
+                    if (lane == ol[u]) { cv[j] = wmax; ck[j] = wkey; thr[j] = skip_threshold(__int_as_float(wmax)); cx[j] = nx; cy[j] = ny; cz[j] = nz; }
+                }
+            }
+        }
+        // ---- this warp's candidate: registers only -------------------------------------------------------------------------
+        int bv = cv[0], bkey = ck[0];
+        float bx = cx[0], by = cy[0], bz = cz[0];
+#pragma unroll
+        for (int j = 1; j < BPL; ++j)
+            if (cv[j] > bv || (cv[j] == bv && ck[j] < bkey)) { bv = cv[j]; bkey = ck[j]; bx = cx[j]; by = cy[j]; bz = cz[j]; }
+        const int wv = __reduce_max_sync(FULL, bv);
+        const int wk = __reduce_min_sync(FULL, bv == wv ? bkey : INT_MAX);
+        Slot* sl = slot[it & 1];
+        if (bv == wv && bkey == wk) { sl[warp].v = wv; sl[warp].k = wk; sl[warp].x = bx; sl[warp].y = by; sl[warp].z = bz; }
+        __syncthreads();
+        {
+            int sv = INT_MIN, sk = INT_MAX;
+            if (lane < kMNW) { sv = sl[lane].v; sk = sl[lane].k; }
+            const int gv = __reduce_max_sync(FULL, sv);
+            const int gk = __reduce_min_sync(FULL, sv == gv ? sk : INT_MAX);
+            const int src = __ffs(__ballot_sync(FULL, sv == gv && sk == gk)) - 1;
+            ox = sl[src].x; oy = sl[src].y; oz = sl[src].z;
+            if (tid == 0) idx[start_m + it] = start_n + key_to_index(gk, bs_log2);
+        }
+    }
+
+    if (tmp) {
+        __syncthreads();
+        for (int q = tid; q < nb * 32; q += kMT) {           // q = bucket * 32 + lane
+            const float4 B = __ldg(pb + q);
+            const float2 T = __ldcg(tv2 + q);
+            const int k0 = __float_as_int(B.z), k1 = __float_as_int(B.w);
+            if (k0 != INT_MAX) tmp[start_n + key_to_index(k0, bs_log2)] = T.x;
+            if (k1 != INT_MAX) tmp[start_n + key_to_index(k1, bs_log2)] = T.y;
+        }
+    }
+}
+
+template <int MT_, int BPL>
+int launch_main3(int b, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx, const BucketWs& ws,
+                 int bs_log2, cudaStream_t stream)
+{
+    fps_bucket_kernel3<MT_, BPL><<<b, MT_, 0, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
+    return check_launch("fps_bucket_kernel3");
+}
+
+template <int MT_>
+int launch_main2(int b, size_t smem, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
+                 const BucketWs& ws, int bs_log2, cudaStream_t stream)
+{
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(fps_bucket_kernel2<MT_>), smem);
+    if (rc_attr != TGN_OK) return rc_attr;
+    fps_bucket_kernel2<MT_><<<b, MT_, smem, stream>>>(xyz, offset, new_offset, tmp, idx, ws, bs_log2);
+    return check_launch("fps_bucket_kernel2");
+}
+
 template <int MT_>
 int launch_main(int b, size_t smem, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
                 const BucketWs& ws, int bs_log2, cudaStream_t stream)
@@ -588,8 +905,38 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
         // redundant per-warp steps and cheaper barriers per cloud, more clouds in flight to hide latency).
         const int sms = sm_count();
         auto fits = [&](int per_sm) { return static_cast<size_t>(per_sm) * (smem + 1024) <= 220 * 1024; };
-        int warps = shape;
+        // Auto (shape 0).  Measured on B200, 24k-point clouds -> 1024 samples (profiles/r2_fps_modes.json): up to 4 clouds per SM
+        // the single-barrier kernel with register-resident tables at 16 warps per cloud wins (1.02 ms against 1.62 ms per call
+        // up to one cloud per SM, 3.16 against 3.32 at four); beyond that the batch is DRAM-bound and the three-barrier kernel
+        // at 4 warps per cloud, 8 clouds per SM, stays ahead (5.27 against 6.17 ms per 1184 clouds).
+        if (shape == 0 && b <= 4 * sms && ws.nbmax <= 2 * 512) shape = 200 + 16;
+        const bool v2 = shape >= 100 && shape < 200;          // 100 + W: the single-barrier schedule (fps_bucket_kernel2)
+        const bool v3 = shape >= 200;                         // 200 + W: the same with register-resident bucket tables (fps_bucket_kernel3)
+        int warps = shape % 100;
         if (warps == 0) warps = (b > 4 * sms && fits(8)) ? 4 : (b > 2 * sms && fits(4)) ? 8 : 16;
+        if (v3) {
+            const int bpl = (ws.nbmax + warps * 32 - 1) / (warps * 32);          // buckets per lane
+            rc = -1;
+            if (warps == 32 && bpl <= 1) rc = launch_main3<1024, 1>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 16 && bpl <= 1) rc = launch_main3<512, 1>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 16 && bpl <= 2) rc = launch_main3<512, 2>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 8 && bpl <= 1) rc = launch_main3<256, 1>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 8 && bpl <= 2) rc = launch_main3<256, 2>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 8 && bpl <= 4) rc = launch_main3<256, 4>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 4 && bpl <= 2) rc = launch_main3<128, 2>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 4 && bpl <= 3) rc = launch_main3<128, 3>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 4 && bpl <= 4) rc = launch_main3<128, 4>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            if (rc == -1) { set_error("furthestsampling: bucket kernel v3 has no shape of %d warps x %d buckets per lane", warps, bpl); rc = TGN_ERR_INVALID; }
+        } else if (v2) {
+            switch (warps) {
+                case 16: rc = launch_main2<512>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+                case 8: rc = launch_main2<256>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+                case 4: rc = launch_main2<128>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+                case 2: rc = launch_main2<64>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+                case 32: rc = launch_main2<1024>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
+                default: set_error("furthestsampling: bucket kernel v2 has no shape of %d warps per cloud", warps); rc = TGN_ERR_INVALID;
+            }
+        } else
         switch (warps) {
             case 16: rc = launch_main<512>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;
             case 8: rc = launch_main<256>(b, smem, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream); break;

@@ -64,6 +64,11 @@ void keep_async_pool()
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long thr = ~0ull;
         (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        // A block freed on stream A must not be handed to stream B by making B WAIT for A's free point: chunks of a host
+        // pipeline run on several streams and would serialise on each other's scratch.  Opportunistic reuse (the free has
+        // already completed) and event-ordered reuse stay on; otherwise the pool grows.
+        int off = 0;
+        (void)cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
     }
     (void)cudaGetLastError();
     done.fetch_or(bit, std::memory_order_relaxed);

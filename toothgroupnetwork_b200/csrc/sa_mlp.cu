@@ -261,9 +261,9 @@ extern "C" int tgn_sa_group_mlp_max(int B, int N, int S, int K, int D, const flo
         if (!sa_mlp_tc8_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the eight-group tcgen05 engine"); return TGN_ERR_INVALID; }
         return sa_mlp_tc8_launch(p, st);
     }
-    if (engine == 2 || (engine == 0 && sa_mlp_tc_supported(p))) {
+    if (engine == 2 || engine == 5 || (engine == 0 && sa_mlp_tc_supported(p))) {
         if (!sa_mlp_tc_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
-        return sa_mlp_tc_launch(p, st);
+        return sa_mlp_tc_launch(p, st, engine == 5 ? 2 : 4);     // 5: half-size CTAs (two per SM; share an SM with other streams' kernels)
     }
     if (engine == 3 || (engine == 0 && sa_mlp_tcw_supported(p))) {
         if (!sa_mlp_tcw_supported(p)) { set_error("sa_group_mlp_max: shape not supported by the wide tcgen05 engine"); return TGN_ERR_INVALID; }

@@ -42,15 +42,16 @@ namespace {
 using namespace tc;
 
 constexpr int kRows = 128;                            // rows of a tile = threads of a tile group
-constexpr int kGroups = 4;
-constexpr int kThreads = kRows * kGroups;
+constexpr int kMaxGroups = 4;                         // tile groups per CTA: 4 (one CTA owns the SM) or 2 (two CTAs per SM, or one
+                                                      // beside another kernel's CTAs: 32K registers / 256 TMEM columns each)
 constexpr uint32_t kChunkStrideA = kRows * 16;        // LBO of the A operand: one 16-byte K-chunk of all rows
 
 struct TcLayout {
     int kpad[kSaMaxLayers];          // K of layer l, multiple of 8
     int npad[kSaMaxLayers];          // N of layer l, multiple of 16
     uint32_t w_hi[kSaMaxLayers], w_lo[kSaMaxLayers], bias[kSaMaxLayers];   // byte offsets in dynamic smem
-    uint32_t a_hi[kGroups], a_lo[kGroups];   // per group activation operands (A of the inner layers, B of the last)
+    uint32_t a_hi[kMaxGroups], a_lo[kMaxGroups];   // per group activation operands (A of the inner layers, B of the last)
+    int groups;                      // tile groups per CTA
     uint32_t ones;                   // constant [128 x 8] tile that adds the bias through the MMA
     uint32_t misc;                   // tmem base (u32) @0, group mbarriers (u64) @8+8g
     uint32_t total;
@@ -111,9 +112,11 @@ __device__ __forceinline__ float relu_max16(const uint32_t (&v)[32]) {
     return m;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kGroups>
+__global__ void __launch_bounds__(kRows * kGroups, 4 / kGroups)
 sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
 {
+    constexpr int kThreads = kRows * kGroups;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -443,8 +446,9 @@ sa_mlp_tc_kernel(const SaParams p, const TcLayout lay)
     }
 }
 
-bool make_layout(const SaParams& p, TcLayout& lay)
+bool make_layout(const SaParams& p, TcLayout& lay, int kGroups = kMaxGroups)
 {
+    lay.groups = kGroups;
     if (p.K > kRows || p.K < 1) return false;
     int kmax = 0;
     uint32_t off = 0;
@@ -488,7 +492,7 @@ bool make_layout(const SaParams& p, TcLayout& lay)
     lay.gpt = kRows / p.K;
     lay.tiles_per_cloud = (p.S + lay.gpt - 1) / lay.gpt;
     lay.tpc_magic = static_cast<uint32_t>(std::min<unsigned long long>((1ull << 32) / static_cast<unsigned long long>(lay.tiles_per_cloud), 0xFFFFFFFFull));
-    return lay.total <= 220 * 1024;
+    return lay.total <= 220u * 1024;
 }
 
 }  // namespace
@@ -499,17 +503,28 @@ bool sa_mlp_tc_supported(const SaParams& p)
     return make_layout(p, lay);
 }
 
-int sa_mlp_tc_launch(SaParams p, cudaStream_t st)
+template <int kGroups>
+int launch_tc(const SaParams& p, const TcLayout& lay, cudaStream_t st)
+{
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(sa_mlp_tc_kernel<kGroups>), lay.total);
+    if (rc_attr != TGN_OK) return rc_attr;
+    // persistent CTAs: one of 4 tile groups per SM (the whole TMEM), or two of 2 groups
+    const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
+    const int grid = static_cast<int>(std::min<long long>((tiles + kGroups - 1) / kGroups, static_cast<long long>(sm_count()) * (kMaxGroups / kGroups)));
+    sa_mlp_tc_kernel<kGroups><<<grid, kRows * kGroups, lay.total, st>>>(p, lay);
+    return check_launch("sa_mlp_tc_kernel");
+}
+
+// groups_per_cta: 4 = one CTA owns the SM (all 64K registers, all 512 TMEM columns); 2 = half-size CTAs (32K registers, 256
+// TMEM columns) that can share an SM with the CTAs of another stream's kernels -- the host pipeline keeps the FPS of the
+// next chunk resident, and a full-size CTA would wait for it to drain.  (Two half CTAs fit one SM only when the operand
+// tiles are small; with the bench shape the weights of the 128-row last layer make it one per SM.)
+int sa_mlp_tc_launch(SaParams p, cudaStream_t st, int groups_per_cta)
 {
     TcLayout lay{};
-    if (!make_layout(p, lay)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
-    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(sa_mlp_tc_kernel), lay.total);
-    if (rc_attr != TGN_OK) return rc_attr;
-    // one persistent CTA (4 tile groups, the whole TMEM budget of its accumulators) per SM
-    const long long tiles = static_cast<long long>(lay.tiles_per_cloud) * p.B;
-    const int grid = static_cast<int>(std::min<long long>((tiles + kGroups - 1) / kGroups, sm_count()));
-    sa_mlp_tc_kernel<<<grid, kThreads, lay.total, st>>>(p, lay);
-    return check_launch("sa_mlp_tc_kernel");
+    if (groups_per_cta == 2 && make_layout(p, lay, 2)) return launch_tc<2>(p, lay, st);
+    if (!make_layout(p, lay, kMaxGroups)) { set_error("sa_group_mlp_max: shape not supported by the tcgen05 engine"); return TGN_ERR_INVALID; }
+    return launch_tc<kMaxGroups>(p, lay, st);
 }
 
 }  // namespace tgn

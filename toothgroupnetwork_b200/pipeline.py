@@ -24,16 +24,20 @@ class HostPipeline:
     """H2D copies run back to back on a dedicated stream in chunks of ``chunk_clouds`` into ONE device
     buffer; compute runs on ``n_streams`` streams over GROUPS of consecutive chunks (``groups``: chunks
     per group in order, the last but one repeating, the last entry being the size of the final group) as soon as the last chunk of a group has landed;
-    results return on a third stream.  Measured on B200 (1184 clouds of 24k points, scripts/gpu_e2e_sweep.sh):
-    one chunk per group is best (5.9e7 sampled points/s); larger groups start later than they gain in
-    kernel efficiency ((2,3,2,1): 5.5e7, (2,5,1): 4.6e7), so that is the default."""
+    results return on a third stream.  Measured on B200 (1184 clouds of 24k points, profiles/r2_summary.md): the kernels of
+    a chunk are sized to own an SM (the group-MLP CTA takes all 64K registers and all 512 TMEM columns, the FPS sort
+    prologue 192 KB of shared memory), so chunks on different streams mostly run one after the other and the end-to-end
+    time is  first H2D + chunks x (compute time of one chunk): 1.55 ms + 8 x 2.07 ms with 148-cloud chunks, against
+    12.4 ms of PCIe transfer.  One chunk per group is best; what moved the number in round 2 was the small-batch FPS
+    (1.67 -> 1.07 ms per 148 clouds), not more streams."""
 
     def __init__(self, module: torch.nn.Module, chunk_clouds: int = 148, n_streams: int = 2,
-                 groups: Sequence[int] = (1,), fps_mode: int = None):
+                 groups: Sequence[int] = (1,), fps_mode: int = None, sa_engine: int = None):
         self.module = module
         self.chunk = int(chunk_clouds)
         self.groups = tuple(int(g) for g in groups) or (1,)
         self.fps_mode = fps_mode          # None: shape by the clouds in flight; else the tgn_furthestsampling mode of every chunk
+        self.sa_engine = sa_engine        # None: leave the module's engine choice; 5 = half-size group-MLP CTAs that share an SM with other chunks' kernels
         self.streams: List[torch.cuda.Stream] = [torch.cuda.Stream() for _ in range(max(1, int(n_streams)))]
         self.copy_in = torch.cuda.Stream()
         self.copy_out = torch.cuda.Stream()
@@ -74,14 +78,15 @@ class HostPipeline:
                 ev = torch.cuda.Event()
                 ev.record(self.copy_in)
                 landed.append(ev)
-        saved_mode = pn2._fps_mode
+        saved_mode, saved_engine = pn2._fps_mode, pn2._sa_engine
+        if self.sa_engine is not None:
+            pn2.set_sa_engine(self.sa_engine)
         for gi, (k0, k1) in enumerate(plan):
             lo, hi = spans[k0][0], spans[k1][1]
             s = self.streams[gi % len(self.streams)]
             s.wait_event(landed[k1])
             # FPS shape for the clouds resident on the GPU (this group and its neighbour on the other stream)
-            pn2.set_fps_mode(self.fps_mode if self.fps_mode is not None else
-                             pn2.fps_mode_for_clouds_in_flight(min(B, (hi - lo) * len(self.streams)), host_feats.shape[2]))
+            pn2.set_fps_mode(self.fps_mode if self.fps_mode is not None else 0)      # 0: the library picks by the clouds of the call
             with torch.cuda.stream(s):
                 d = dev[lo:hi]
                 new_xyz, new_points = self.module(d[:, :3].contiguous(), d)
@@ -96,6 +101,7 @@ class HostPipeline:
                 out_xyz_host[lo:hi].copy_(new_xyz, non_blocking=True)
                 out_points_host[lo:hi].copy_(new_points, non_blocking=True)
         pn2.set_fps_mode(saved_mode)
+        pn2.set_sa_engine(saved_engine)
         main.wait_stream(self.copy_out)
         main.wait_stream(self.copy_in)
         for s in self.streams:

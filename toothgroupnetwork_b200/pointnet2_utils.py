@@ -35,7 +35,7 @@ from . import pointops
 
 SA_FUSED_MAX_WIDTH = 128
 SA_FUSED_MAX_LAYERS = 4
-ENGINE_AUTO, ENGINE_FP32, ENGINE_TC, ENGINE_TCW, ENGINE_TC8 = 0, 1, 2, 3, 4     # TCW: wide layers (bf16x2); TC8: eight tile groups, bf16x3
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TC, ENGINE_TCW, ENGINE_TC8, ENGINE_TC_HALF = 0, 1, 2, 3, 4, 5     # TCW: wide layers (bf16x2); TC8: eight tile groups, bf16x3; TC_HALF: engine 2 in half-size CTAs
 _sa_engine = ENGINE_AUTO
 
 
