@@ -8,8 +8,9 @@ TAILN=25 run t_live $PT tests/test_gpu_reference_live.py
 TAILN=15 run t_pointnet2 $PT tests/test_gpu_pointnet2.py
 TAILN=15 run t_pointops  $PT tests/test_gpu_pointops.py
 run t_callers $PT tests/test_gpu_callers.py
+run t_crops $PT tests/test_gpu_crops.py
 run smoke python __graft_entry__.py smoke
 TAILN=3 run bench python bench.py --steps 10 --warmup 3
 TAILN=3 run bench_ref python bench.py --impl reference --steps 2 --warmup 1
-TMO=900 run op_bench python scripts/op_bench.py --out gpurun_out/op_bench.json --sections knn,sa,fp
+TMO=900 run op_bench python scripts/op_bench.py --out gpurun_out/op_bench.json --sections fps,knn,ball,sa,fp
 TMO=900 run model_parity python scripts/model_parity.py --out gpurun_out/model_parity.json
