@@ -36,6 +36,8 @@
 #include "fps.cuh"
 #include "tgn_b200.h"
 
+#include <cstdio>
+
 namespace tgn {
 namespace {
 
@@ -507,7 +509,9 @@ int tgn_furthestsampling(int b, int n_max, const float* xyz, const int* offset, 
 void furthestsampling_cuda_launcher(int b, int n, const float* xyz, const int* offset, const int* new_offset, float* tmp,
                                     int* idx)
 {
-    (void)tgn::fps_dispatch(b, n, xyz, offset, new_offset, tmp, idx, 0, static_cast<cudaStream_t>(0));
+    // void like the reference's launcher: a rejected call is reported on stderr instead of returning silently
+    if (tgn::fps_dispatch(b, n, xyz, offset, new_offset, tmp, idx, 0, static_cast<cudaStream_t>(0)) != TGN_OK)
+        std::fprintf(stderr, "libtgn_b200: %s\n", tgn_last_error());
 }
 
 }  // extern "C"

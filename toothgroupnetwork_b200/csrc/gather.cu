@@ -12,6 +12,13 @@
 #include "common.cuh"
 #include "tgn_b200.h"
 
+// The reference's launchers return void: a rejected call cannot be signalled to the caller, so say it on stderr
+// instead of returning with the outputs untouched.
+#ifndef TGN_REPORT
+#include <cstdio>
+#define TGN_REPORT(call) do { if ((call) != TGN_OK) std::fprintf(stderr, "libtgn_b200: %s\n", tgn_last_error()); } while (0)
+#endif
+
 namespace tgn {
 namespace {
 
@@ -389,20 +396,20 @@ int tgn_transpose_cn(int B, int C, int N, const float* in, float* out, void* str
 
 // ---- the reference's own launcher names (legacy default stream, no status) -----------------
 void grouping_forward_cuda_launcher(int m, int nsample, int c, const float* input, const int* idx, float* output)
-{ (void)tgn_grouping_forward(m, nsample, c, input, idx, output, nullptr); }
+{ TGN_REPORT(tgn_grouping_forward(m, nsample, c, input, idx, output, nullptr)); }
 void grouping_backward_cuda_launcher(int m, int nsample, int c, const float* grad_output, const int* idx, float* grad_input)
-{ (void)tgn_grouping_backward(m, nsample, c, grad_output, idx, grad_input, nullptr); }
+{ TGN_REPORT(tgn_grouping_backward(m, nsample, c, grad_output, idx, grad_input, nullptr)); }
 void interpolation_forward_cuda_launcher(int n, int c, int k, const float* input, const int* idx, const float* weight, float* output)
-{ (void)tgn_interpolation_forward(n, c, k, input, idx, weight, output, nullptr); }
+{ TGN_REPORT(tgn_interpolation_forward(n, c, k, input, idx, weight, output, nullptr)); }
 void interpolation_backward_cuda_launcher(int n, int c, int k, const float* grad_output, const int* idx, const float* weight, float* grad_input)
-{ (void)tgn_interpolation_backward(n, c, k, grad_output, idx, weight, grad_input, nullptr); }
+{ TGN_REPORT(tgn_interpolation_backward(n, c, k, grad_output, idx, weight, grad_input, nullptr)); }
 void subtraction_forward_cuda_launcher(int n, int nsample, int c, const float* input1, const float* input2, const int* idx, float* output)
-{ (void)tgn_subtraction_forward(n, nsample, c, input1, input2, idx, output, nullptr); }
+{ TGN_REPORT(tgn_subtraction_forward(n, nsample, c, input1, input2, idx, output, nullptr)); }
 void subtraction_backward_cuda_launcher(int n, int nsample, int c, const int* idx, const float* grad_output, float* grad_input1, float* grad_input2)
-{ (void)tgn_subtraction_backward(n, nsample, c, idx, grad_output, grad_input1, grad_input2, nullptr); }
+{ TGN_REPORT(tgn_subtraction_backward(n, nsample, c, idx, grad_output, grad_input1, grad_input2, nullptr)); }
 void aggregation_forward_cuda_launcher(int n, int nsample, int c, int w_c, const float* input, const float* position, const float* weight, const int* idx, float* output)
-{ (void)tgn_aggregation_forward(n, nsample, c, w_c, input, position, weight, idx, output, nullptr); }
+{ TGN_REPORT(tgn_aggregation_forward(n, nsample, c, w_c, input, position, weight, idx, output, nullptr)); }
 void aggregation_backward_cuda_launcher(int n, int nsample, int c, int w_c, const float* input, const float* position, const float* weight, const int* idx, const float* grad_output, float* grad_input, float* grad_position, float* grad_weight)
-{ (void)tgn_aggregation_backward(n, nsample, c, w_c, input, position, weight, idx, grad_output, grad_input, grad_position, grad_weight, nullptr); }
+{ TGN_REPORT(tgn_aggregation_backward(n, nsample, c, w_c, input, position, weight, idx, grad_output, grad_input, grad_position, grad_weight, nullptr)); }
 
 }  // extern "C"

@@ -23,6 +23,13 @@
 #include "common.cuh"
 #include "tgn_b200.h"
 
+// The reference's launchers return void: a rejected call cannot be signalled to the caller, so say it on stderr
+// instead of returning with the outputs untouched.
+#ifndef TGN_REPORT
+#include <cstdio>
+#define TGN_REPORT(call) do { if ((call) != TGN_OK) std::fprintf(stderr, "libtgn_b200: %s\n", tgn_last_error()); } while (0)
+#endif
+
 namespace tgn {
 namespace {
 
@@ -231,7 +238,7 @@ int tgn_knnquery(int b, int m, int nsample, const float* xyz, const float* new_x
 void knnquery_cuda_launcher(int m, int nsample, const float* xyz, const float* new_xyz, const int* offset,
                             const int* new_offset, int* idx, float* dist2)
 {
-    (void)tgn_knnquery(INT_MAX, m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, nullptr);
+    TGN_REPORT(tgn_knnquery(INT_MAX, m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, nullptr));
 }
 
 }  // extern "C"
