@@ -122,6 +122,43 @@ def test_dropin_shim_resolves_reference_import_paths():
         dropin.uninstall()
 
 
+def test_dropin_serves_the_reference_real_model_files():
+    """The reference's unmodified models/modules/*.py import and CONSTRUCT on this package through dropin.install()
+    (parameter counts of SURVEY.md 8c), with this package's classes inside; needs the reference checkout or its staged archive."""
+    import pytest
+    import torch
+    from oracle import ref_models
+    if not ref_models.available():
+        pytest.skip("reference snapshot not staged")
+    w = ref_models.World("b200")
+    count = lambda m: sum(q.numel() for q in m.parameters())
+    with w:
+        pp = w.mod("models.modules.pointnet_pp").get_model()
+        assert count(pp) == 8957689 and type(pp.sa1).__module__ == "toothgroupnetwork_b200.pointnet2_utils"
+        assert type(pp.fp1).__module__ == "toothgroupnetwork_b200.pointnet2_utils"
+        assert count(w.mod("models.modules.tsg_centroid_module").get_model()) == 832660
+        seg = w.mod("models.modules.tsg_seg_module").get_model()
+        assert count(seg) == 1542325 and seg.flatten_sa.group_all
+        blocks = w.mod("models.modules.cbl_point_transformer.blocks")
+        assert blocks.pointops.__name__ == "toothgroupnetwork_b200.pointops"
+        saved = torch.nn.Module.cuda
+        torch.nn.Module.cuda = lambda self, *a, **k: self           # grouping_network_module.py:15 calls .cuda() in __init__
+        try:
+            g = w.mod("models.modules.grouping_network_module").GroupingNetworkModule(
+                {"model_parameter": {"input_feat": 6, "stride": [1, 4, 4, 4, 4], "nsample": [36, 24, 24, 24, 24], "blocks": [2, 3, 4, 6, 3],
+                                     "block_num": 5, "planes": [32, 64, 128, 256, 512], "crop_sample_size": 3072}})
+        finally:
+            torch.nn.Module.cuda = saved
+        assert count(g) == 15729246
+        # the crop search of ops_utils is served by the GPU version too
+        assert w.mod("ops_utils").get_nearest_neighbor_idx.__module__ == "toothgroupnetwork_b200.crops"
+    # state_dict keys are the reference's (checkpoints load unchanged)
+    ref = ref_models.World("reference", cpu_dry_run=True)
+    with ref:
+        want = set(ref.mod("models.modules.pointnet_pp").get_model().state_dict().keys())
+    assert set(pp.state_dict().keys()) == want
+
+
 def test_square_distance_matches_oracle_bitwise_on_cpu():
     from oracle import oracle
     from toothgroupnetwork_b200 import clouds
