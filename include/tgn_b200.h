@@ -158,6 +158,10 @@ int tgn_three_nn(int B, int N, int S, const float *xyz1, const float *xyz2, floa
 /* Same with `order`: bit 0 / bit 1 = |xyz1|^2 / |xyz2|^2 in the contiguous-reduce rounding (see tgn_ball_query). */
 int tgn_three_nn_ex(int B, int N, int S, const float *xyz1, const float *xyz2, float *dist, int *idx, int order, void *stream);
 
+/* The matrix itself (pointnet2_utils.square_distance :20-41): src (B,N,3), dst (B,M,3) -> out (B,N,M), expanded form, `order` as in
+ * tgn_three_nn_ex (bit 0: src, bit 1: dst).  Forward only; the Python wrapper keeps torch's formulation under autograd. */
+int tgn_square_distance(int B, int N, int M, const float *src, const float *dst, float *out, int order, void *stream);
+
 /* Weighted 3-point interpolation (pointnet2_utils.py:337-340): weights 1/(dist+1e-8) normalised,
  * points2 (B,S,C) point-major -> out (B,N,C). */
 int tgn_three_interpolate(int B, int N, int S, int C, const float *points2, const float *dist, const int *idx,

@@ -74,6 +74,35 @@ def test_ball_query_bit_exact_vs_reference_on_gpu(B, r, K, pattern):
 
 
 @pytest.mark.parametrize("pattern", ["views", "contiguous", "mixed"])
+def test_square_distance_kernel_bitwise_vs_reference_on_gpu(pattern):
+    """pointnet2_utils.square_distance (:20-41) as the losses and tsegnet.get_ddf call it: the kernel against the reference's
+    matmul + two reductions on the GPU, for the layouts that change torch's |p|^2 rounding."""
+    feats = arch(2, 6000)
+    a = feats[:, :3, :].permute(0, 2, 1)                   # strided view (B,N,3)
+    b = a[:, :512, :].contiguous()
+    if pattern == "contiguous":
+        a = a.contiguous()
+    elif pattern == "views":
+        b = b.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    with world("reference"):
+        want = refpn().square_distance(a, b)
+    before = pn2.L.launch_count()
+    got = pn2.square_distance(a, b)
+    assert pn2.L.launch_count() == before + 1
+    assert torch.equal(got, want)
+    # tsegnet.get_ddf (tsegnet.py:24-33): crops (8,3072,3) as a permuted view against one centre each, (1,8,3).permute(1,0,2)
+    crops = feats[:1, :3, :3072].expand(8, 3, 3072).contiguous().permute(0, 2, 1)
+    centres = torch.rand(1, 8, 3, device="cuda").permute(1, 0, 2)
+    with world("reference"):
+        want = refpn().square_distance(crops, centres)
+    assert torch.equal(pn2.square_distance(crops, centres), want)
+    # under autograd the torch formulation is kept (the losses differentiate through it)
+    ag = a.clone().requires_grad_(True)
+    pn2.square_distance(ag, b).sum().backward()
+    assert ag.grad is not None
+
+
+@pytest.mark.parametrize("pattern", ["views", "contiguous", "mixed"])
 def test_three_nn_bit_exact_vs_reference_on_gpu(pattern):
     feats = arch(2, 24000)
     x1 = feats[:, :3, :].permute(0, 2, 1)

@@ -39,6 +39,7 @@ _SIGS = {
     "tgn_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp],
     "tgn_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tgn_three_nn_ex": [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
+    "tgn_square_distance": [_i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "tgn_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tgn_three_interpolate_ex": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "tgn_gather_rows": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],

@@ -269,6 +269,24 @@ three_interpolate_kernel(int N, int S, int C, const float* __restrict__ points2,
     }
 }
 
+// out[b, i, j] = expanded squared distance between src[b, i] and dst[b, j] (pointnet2_utils.square_distance :20-41), the
+// same arithmetic as the searches above but materialised: the losses (tgn_loss.py / tsg_loss.py) and tsegnet.get_ddf want the
+// matrix itself.  One thread per output element, src row staged per block row.
+__global__ void __launch_bounds__(256)
+square_distance_kernel(int N, int M, const float* __restrict__ src, const float* __restrict__ dst, float* __restrict__ out, int order)
+{
+    const int b = blockIdx.z, i = blockIdx.y;
+    const float* a = src + 3 * (static_cast<size_t>(b) * N + i);
+    const float ax = __ldg(a), ay = __ldg(a + 1), az = __ldg(a + 2);
+    const float an = sq_norm_unfused(ax, ay, az, order & 1);
+    float* row = out + (static_cast<size_t>(b) * N + i) * M;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < M; j += gridDim.x * 256) {
+        const float* p = dst + 3 * (static_cast<size_t>(b) * M + j);
+        const float bx = __ldg(p), by = __ldg(p + 1), bz = __ldg(p + 2);
+        row[j] = sq_dist_expanded(ax, ay, az, an, bx, by, bz, sq_norm_unfused(bx, by, bz, order & 2));
+    }
+}
+
 }  // namespace
 }  // namespace tgn
 
@@ -362,6 +380,16 @@ int tgn_three_nn_ex(int B, int N, int S, const float* xyz1, const float* xyz2, f
     dim3 grid((N + 127) / 128, B);
     three_nn_kernel<128><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(N, S, xyz1, xyz2, dist, idx, order);
     return check_launch("three_nn_kernel");
+}
+
+int tgn_square_distance(int B, int N, int M, const float* src, const float* dst, float* out, int order, void* stream)
+{
+    using namespace tgn;
+    if (B <= 0 || N <= 0 || M <= 0) return TGN_OK;
+    if (B > 65535 || N > 65535) { set_error("square_distance: B=%d / N=%d exceed the grid limits", B, N); return TGN_ERR_INVALID; }
+    dim3 grid(std::min((M + 255) / 256, 64), N, B);
+    square_distance_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(N, M, src, dst, out, order);
+    return check_launch("square_distance_kernel");
 }
 
 int tgn_three_interpolate(int B, int N, int S, int C, const float* points2, const float* dist, const int* idx, float* out,

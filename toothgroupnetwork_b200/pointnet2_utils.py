@@ -110,11 +110,18 @@ class _GatherRows(Function):
 
 def square_distance(src, dst):
     """:20-41.  (B,N,C),(B,M,C) -> (B,N,M) in the expanded form -2ab + |a|^2 + |b|^2.
-    Dense library ops (this is the reference's own formulation; it is differentiable and only
-    the losses call it on a handful of centroids).  The neighbourhood searches below never
-    materialise this matrix."""
-    B, N, _ = src.shape
+    CUDA float32 3-D coordinates without autograd: one kernel with the reference's arithmetic (the rounding of |p|^2 follows
+    the operands' layouts like torch's own reduction does, see ``_alt``) -- bit-identical to the torch formulation below,
+    which stays for everything else (CPU tensors, other C, gradients: the losses differentiate through it)."""
+    B, N, C = src.shape
     M = dst.shape[1]
+    if (C == 3 and src.is_cuda and dst.is_cuda and src.dtype == torch.float32 and dst.dtype == torch.float32
+            and N <= 65535 and B <= 65535 and not (torch.is_grad_enabled() and (src.requires_grad or dst.requires_grad))):
+        order = _alt(src) | (_alt(dst) << 1)
+        s, d = src.contiguous(), dst.contiguous()
+        out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+        L.call("tgn_square_distance", B, N, M, L.ptr(s), L.ptr(d), L.ptr(out), order, L.stream_ptr())
+        return out
     dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
     dist += torch.sum(src ** 2, -1).view(B, N, 1)
     dist += torch.sum(dst ** 2, -1).view(B, 1, M)
@@ -226,6 +233,11 @@ def set_reference_device(device: str) -> None:
 def _alt(t: torch.Tensor) -> int:
     """1 when torch.sum(t ** 2, -1) of this (..., 3) tensor would take the contiguous-reduce rounding."""
     return 1 if (_reference_device == "cuda" and t.is_contiguous()) else 0
+
+
+def _alt_fresh() -> int:
+    """The same for a tensor fresh out of index_points (always contiguous)."""
+    return 1 if _reference_device == "cuda" else 0
 
 
 def _to_point_major(x: torch.Tensor) -> torch.Tensor:
@@ -608,7 +620,7 @@ class PointNetSetAbstraction(nn.Module):
     def forward(self, xyz, points):
         """xyz (B,3,N), points (B,D,N) or None -> new_xyz (B,3,S), new_points (B,C_out,S)."""
         L.require_cuda(xyz, points)
-        order = 1 | (_alt(xyz.permute(0, 2, 1)) << 1)             # new_xyz (index_points output) contiguous; xyz as the reference sees it
+        order = _alt_fresh() | (_alt(xyz.permute(0, 2, 1)) << 1)   # new_xyz (index_points output) contiguous; xyz as the reference sees it
         xyz_t = _to_point_major(xyz)                              # (B,N,3)
         feats_t = None if points is None else _transpose(points)  # (B,N,D)
         B, N, _ = xyz_t.shape
@@ -679,7 +691,7 @@ class PointNetSetAbstractionMsg(nn.Module):
 
     def forward(self, xyz, points):
         L.require_cuda(xyz, points)
-        order = 1 | (_alt(xyz.permute(0, 2, 1)) << 1)
+        order = _alt_fresh() | (_alt(xyz.permute(0, 2, 1)) << 1)
         xyz_t = _to_point_major(xyz)
         feats_t = None if points is None else _transpose(points)
         B, N, _ = xyz_t.shape
