@@ -255,6 +255,34 @@ typedef struct {
     float eps, momentum;
 } tgn_pw_apply_t;
 
+/* Fused forward of blocks.PointTransformerLayer (models/modules/cbl_point_transformer/blocks.py:14-44): vector
+ * self-attention over the K neighbours idx[i, :] of every point, share_planes = 8, in up to four passes over the gathers (one per
+ * BatchNorm that runs on batch statistics + the output pass); nothing of size (n, K, c) is materialised.
+ *   p (n,3); xq, xk, xv (n,c) = linear_q/k/v(x) (left to the caller's GEMMs); idx (n,K) int32 (kNN of p in p); out (n,c)
+ *   linear_p = Linear(3,3) [p_w0 (3,3), p_b0] -> BatchNorm1d(3) [p_*] -> ReLU -> Linear(3,c) [p_w1 (c,3), p_b1]
+ *   linear_w = BatchNorm1d(c) [a_gamma..] -> ReLU -> Linear(c, c/8) [a_w (c/8,c), a_b] -> BatchNorm1d(c/8) [b_gamma..] -> ReLU
+ *              -> Linear(c/8, c/8) [b_w, b_b]
+ *   bn_mode[i]: 1 = batch statistics (stats_* = zeroed fp64 {sum[ch], sumsq[ch]} scratch, filled by the passes), 2 = running
+ *   statistics; update_running != 0 applies torch's momentum update to the *_rmean / *_rvar of the BatchNorms in mode 1.
+ * c in {32, 64, 128, 256, 512}, K <= 64. */
+typedef struct {
+    int n, c, K;
+    const float *p, *xq, *xk, *xv;
+    const int *idx;
+    float *out;
+    const float *p_w0, *p_b0, *p_w1, *p_b1;
+    const float *p_gamma, *p_beta; float *p_rmean, *p_rvar; float p_eps, p_momentum;
+    const float *a_gamma, *a_beta; float *a_rmean, *a_rvar; float a_eps, a_momentum;
+    const float *a_w, *a_b;
+    const float *b_gamma, *b_beta; float *b_rmean, *b_rvar; float b_eps, b_momentum;
+    const float *b_w, *b_b;
+    double *stats_p, *stats_a, *stats_b;
+    int bn_mode[3];
+    int update_running;
+} tgn_pt_layer_t;
+int tgn_pt_layer_forward(const tgn_pt_layer_t *layer, void *stream);
+int tgn_pt_layer_struct_size(void);
+
 size_t tgn_pw_packed_bytes(int cout, int cin);
 int tgn_pw_struct_size(int which);         /* sizeof(tgn_pw_layer_t) (0) / sizeof(tgn_pw_apply_t) (1): binding self-check */
 int tgn_pw_pack_weights(int cout, int cin, const float *w, void *packed, void *stream);

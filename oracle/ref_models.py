@@ -192,7 +192,7 @@ class World:
     to that world's modules.
     """
 
-    def __init__(self, ops: str, cpu_dry_run: bool = False, accelerate_crops: bool = True):
+    def __init__(self, ops: str, cpu_dry_run: bool = False, accelerate_crops: bool = True, fused_blocks: bool = True):
         assert ops in ("reference", "b200")
         self.ops = ops
         root = reference_root()
@@ -214,6 +214,10 @@ class World:
                 # the crop search between the two stages (sklearn KDTree on the host in the reference) on the GPU too
                 from toothgroupnetwork_b200 import crops
                 crops.accelerate(sys.modules["ops_utils"])
+            if ops == "b200" and fused_blocks:
+                # no-grad forwards of PointTransformerLayer / TransitionDown on the fused kernels (autograd keeps the reference's code)
+                from toothgroupnetwork_b200 import blocks_fused
+                blocks_fused.accelerate(sys.modules["models.modules.cbl_point_transformer.blocks"])
         finally:
             self.modules = _purge()
             sys.path.remove(root)

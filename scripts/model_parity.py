@@ -133,6 +133,37 @@ class float64_reference:
         self.pn.farthest_point_sample, self.pn.query_ball_point = self.saved
 
 
+class float64_point_transformer:
+    """The same for the packed-layout operators of the point-transformer models: FPS and kNN see the float32 coordinates, the
+    3-NN interpolation of the decoder keeps float64 (the reference's own accumulates into a FloatTensor, pointops.py:160-180)."""
+
+    def __init__(self, world):
+        self.po = world.mod("external_libs.pointops.functions.pointops")
+
+    def __enter__(self):
+        po = self.po
+        self.saved = (po.furthestsampling, po.knnquery, po.interpolation)
+        fps, knn, _ = self.saved
+        po.furthestsampling = lambda xyz, off, noff: fps(xyz.float().contiguous(), off, noff)
+
+        def knn64(k, xyz, new_xyz, off, noff):
+            idx, _ = knn(k, xyz.float().contiguous(), (xyz if new_xyz is None else new_xyz).float().contiguous(), off, noff)
+            q = xyz if new_xyz is None else new_xyz
+            d = (xyz[idx.long().view(-1)].view(idx.shape[0], idx.shape[1], 3) - q.unsqueeze(1)).pow(2).sum(-1).sqrt()
+            return idx, d
+
+        def interp64(xyz, new_xyz, feat, off, noff, k=3):
+            idx, dist = knn64(k, xyz, new_xyz, off, noff)
+            w = 1.0 / (dist + 1e-8)
+            w = w / w.sum(1, keepdim=True)
+            return (feat[idx.long().view(-1)].view(idx.shape[0], k, -1) * w.unsqueeze(-1)).sum(1)
+
+        po.knnquery, po.interpolation = knn64, interp64
+
+    def __exit__(self, *exc):
+        self.po.furthestsampling, self.po.knnquery, self.po.interpolation = self.saved
+
+
 class Timer:
     def __init__(self):
         self.gpu = torch.cuda.is_available()
@@ -329,6 +360,63 @@ def case_tgn(worlds, feats, labels, timer):
     return res
 
 
+def case_tgn_infer(worlds, feats, labels, train_bn, timer):
+    """GroupingNetworkModule forward under torch.no_grad() (the reference's validation / inference step): in the b200 world the
+    PointTransformerLayer and TransitionDown forwards run on the fused kernels (toothgroupnetwork_b200.blocks_fused)."""
+    outs, coords, times = {}, {}, {}
+    state = None
+    keys = ("sem_1", "offset_1", "first_features", "sem_2", "cropped_feature_ls")
+    for w in worlds:
+        with w, torch.no_grad():
+            torch.manual_seed(0)
+            gm = w.mod("models.modules.grouping_network_module")
+            module = dev(gm.GroupingNetworkModule({"model_parameter": dict(TGN_PARAMS)}))
+            if state is None:
+                state = {k: v.clone() for k, v in module.state_dict().items()}
+            module.train(train_bn)
+            coords[w.ops] = {}
+            hs = hook_sampled_coords(module, coords[w.ops])
+
+            def fwd():
+                module.load_state_dict(state)                      # same running statistics every repetition
+                coords[w.ops].clear()
+                return module([feats, labels])
+
+            o, ms = timer(fwd, warm=1, reps=3)
+            outs[w.ops] = {k: o[k] for k in keys if o.get(k) is not None}
+            outs[w.ops]["nn_crop_indexes"] = torch.from_numpy(np.stack([np.asarray(x) for x in o["nn_crop_indexes"]]).astype(np.int64))
+            times[w.ops] = ms
+            raw_crops = o["nn_crop_indexes"]
+            if w.ops == "b200" and torch.cuda.is_available():
+                from toothgroupnetwork_b200 import blocks_fused
+                blocks_fused.set_enabled(False)
+                try:
+                    _, times["b200_unfused_blocks"] = timer(fwd, warm=1, reps=3)
+                finally:
+                    blocks_fused.set_enabled(True)
+            for h in hs:
+                h.remove()
+            if w.ops == "reference" and torch.cuda.is_available():
+                ou = w.mod("ops_utils")
+                saved_crop = ou.get_nearest_neighbor_idx
+                # the float64 run clusters slightly different offsets: it is handed the float32 run's crops, so that the second
+                # module's outputs are the exact answer for the same crops
+                ou.get_nearest_neighbor_idx = lambda *a, **k: raw_crops
+                try:
+                    with float64_point_transformer(w):
+                        module.load_state_dict(state)
+                        module.double()
+                        o = module([feats.double(), labels])
+                        outs["fp64_truth"] = {k: o[k] for k in keys if o.get(k) is not None}
+                        outs["fp64_truth"]["nn_crop_indexes"] = torch.from_numpy(np.stack([np.asarray(x) for x in o["nn_crop_indexes"]]).astype(np.int64))
+                except Exception as e:                             # the truth leg is an aid, not the gate
+                    print("fp64 truth unavailable:", repr(e)[:300])
+                    outs.pop("fp64_truth", None)
+                finally:
+                    ou.get_nearest_neighbor_idx = saved_crop
+    return finish(outs, coords, times)
+
+
 def finish(outs, coords, times):
     res = {"ms": times}
     if "b200" in outs and "reference" in outs:
@@ -361,7 +449,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "model_parity.json"))
     ap.add_argument("--points", type=int, default=24000)
-    ap.add_argument("--cases", default="pp,tseg,tgn")
+    ap.add_argument("--cases", default="pp,tseg,tgn,tgni")
     ap.add_argument("--cpu-dry-run", action="store_true")
     args = ap.parse_args()
 
@@ -391,6 +479,9 @@ def main():
         report["tsegnet_evalBN"] = case_tseg(worlds, feats, labels, False, timer)
     if "tgn" in cases:
         report["tgnet_fps_fwd_bwd"] = case_tgn(worlds, feats, labels, timer)
+    if "tgni" in cases:
+        report["tgnet_fps_nograd_trainBN"] = case_tgn_infer(worlds, feats, labels, True, timer)
+        report["tgnet_fps_nograd_evalBN"] = case_tgn_infer(worlds, feats, labels, False, timer)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(report, f, indent=1)

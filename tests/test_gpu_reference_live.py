@@ -319,6 +319,79 @@ def test_real_blocks_transition_down_transformer_layer_transition_up():
         assert torch.equal(got, want), (k, float((got - want).abs().max()), float(want.abs().max()))
 
 
+@pytest.mark.parametrize("c,K,n", [(32, 36, 24000), (64, 24, 6000), (128, 24, 1500), (512, 24, 93)])
+@pytest.mark.parametrize("train_bn", [True, False])
+def test_fused_point_transformer_layer_vs_reference_layer(c, K, n, train_bn):
+    """blocks.PointTransformerLayer (:14-44) under no_grad: the fused multi-pass kernel (csrc/pt_layer.cu) against the reference's own
+    layer on the reference's operators, and against that layer evaluated in float64 with the same neighbour indices."""
+    from toothgroupnetwork_b200 import blocks_fused, pointops
+    name = "models.modules.cbl_point_transformer.blocks"
+    p = clouds.dental_arch(n, 4)[0].cuda()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(n, c, device="cuda", generator=g)
+    o = torch.tensor([n], dtype=torch.int32, device="cuda")
+    with world("reference"), torch.no_grad():
+        Bm = world("reference").mod(name)
+        torch.manual_seed(0)
+        ref = Bm.PointTransformerLayer(c, c, 8, K).cuda().train(train_bn)
+        g2 = torch.Generator().manual_seed(3)
+        for b in (ref.linear_p[1], ref.linear_w[0], ref.linear_w[3]):      # non-trivial affine / running statistics
+            b.weight.copy_(torch.rand(b.weight.shape, generator=g2) + 0.5)
+            b.bias.copy_(torch.randn(b.bias.shape, generator=g2) * 0.1)
+            b.running_mean.copy_(torch.randn(b.running_mean.shape, generator=g2) * 0.1)
+            b.running_var.copy_(torch.rand(b.running_var.shape, generator=g2) + 0.5)
+        state = {k: v.clone() for k, v in ref.state_dict().items()}
+        want = ref([p, x, o])
+        ref_state_after = {k: v.clone() for k, v in ref.state_dict().items()}
+        # float64 truth: same layer, same neighbour indices (kNN on the float32 coordinates)
+        ref.load_state_dict(state)
+        po = world("reference").mod("external_libs.pointops.functions.pointops")
+        saved = po.knnquery
+        po.knnquery = lambda k, xyz, new_xyz, off, noff: saved(k, xyz.float().contiguous(), new_xyz.float().contiguous(), off, noff)
+        try:
+            truth = ref.double()([p.double(), x.double(), o])
+        finally:
+            po.knnquery = saved
+            ref.float()
+    with world("b200"), torch.no_grad():
+        ours = world("b200").mod(name).PointTransformerLayer(c, c, 8, K).cuda().train(train_bn)
+        ours.load_state_dict(state)
+        assert blocks_fused.pt_layer_fusable(ours, p, x, o)
+        launches = pn2.L.launch_count()
+        got = ours([p, x, o])
+        assert pn2.L.launch_count() - launches >= 2
+    err, e_ours, e_ref = elementwise(got, want), elementwise(got, truth), elementwise(want, truth)
+    assert err < REL_TOL or e_ours <= max(REL_TOL, 2.0 * e_ref), (err, e_ours, e_ref)
+    if train_bn:
+        for k, v in ref_state_after.items():
+            if "running" in k:
+                assert elementwise(ours.state_dict()[k], v) < 1e-4, k
+            if "num_batches_tracked" in k:
+                assert int(ours.state_dict()[k]) == int(v)
+
+
+@pytest.mark.parametrize("train_bn", [True, False])
+def test_fused_transition_down_vs_reference(train_bn):
+    """blocks.TransitionDown (stride 4, :59-79) under no_grad on the tcgen05 layer chain: same sampled points, features within 1e-4 /
+    the float64 criterion."""
+    name = "models.modules.cbl_point_transformer.blocks"
+    p = torch.cat([clouds.dental_arch(6000, 5)[0], clouds.dental_arch(3000, 6)[0]]).cuda()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(9000, 32, device="cuda", generator=g)
+    o = torch.tensor([6000, 9000], dtype=torch.int32, device="cuda")
+    with world("reference"), torch.no_grad():
+        torch.manual_seed(0)
+        ref = world("reference").mod(name).TransitionDown(32, 64, 4, 24).cuda().train(train_bn)
+        state = {k: v.clone() for k, v in ref.state_dict().items()}
+        p_ref, x_ref, o_ref = ref([p, x, o])
+    with world("b200"), torch.no_grad():
+        ours = world("b200").mod(name).TransitionDown(32, 64, 4, 24).cuda().train(train_bn)
+        ours.load_state_dict(state)
+        p_new, x_new, o_new = ours([p, x, o])
+    assert torch.equal(p_new, p_ref) and torch.equal(o_new, o_ref)
+    assert elementwise(x_new, x_ref) < REL_TOL
+
+
 def test_farthest_point_sample_np_wrapper():
     """pointnet2_utils.farthest_point_sample_np (:103-118; unused by the reference, random start there): numpy in/out,
     deterministic start, same samples as the tensor API."""

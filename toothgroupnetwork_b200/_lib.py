@@ -45,6 +45,7 @@ _SIGS = {
     "tgn_gather_rows": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "tgn_transpose_cn": [_i, _i, _i, _vp, _vp, _vp],
     "tgn_sa_group_mlp_max": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tgn_pt_layer_forward": [_vp, _vp],
     "tgn_pw_pack_weights": [_i, _i, _vp, _vp, _vp],
     "tgn_pw_layer_forward": [_vp, _vp],
     "tgn_pw_apply": [_vp, _vp],
@@ -81,6 +82,22 @@ class PwApply(ctypes.Structure):
     ]
 
 
+class PtLayer(ctypes.Structure):
+    """tgn_pt_layer_t (include/tgn_b200.h)."""
+    _fields_ = [
+        ("n", _i), ("c", _i), ("K", _i),
+        ("p", _vp), ("xq", _vp), ("xk", _vp), ("xv", _vp), ("idx", _vp), ("out", _vp),
+        ("p_w0", _vp), ("p_b0", _vp), ("p_w1", _vp), ("p_b1", _vp),
+        ("p_gamma", _vp), ("p_beta", _vp), ("p_rmean", _vp), ("p_rvar", _vp), ("p_eps", _f), ("p_momentum", _f),
+        ("a_gamma", _vp), ("a_beta", _vp), ("a_rmean", _vp), ("a_rvar", _vp), ("a_eps", _f), ("a_momentum", _f),
+        ("a_w", _vp), ("a_b", _vp),
+        ("b_gamma", _vp), ("b_beta", _vp), ("b_rmean", _vp), ("b_rvar", _vp), ("b_eps", _f), ("b_momentum", _f),
+        ("b_w", _vp), ("b_b", _vp),
+        ("stats_p", _vp), ("stats_a", _vp), ("stats_b", _vp),
+        ("bn_mode", _i * 3), ("update_running", _i),
+    ]
+
+
 # the reference's ten extern "C" launchers (part 1): void return, legacy default stream
 REFERENCE_LAUNCHERS = [
     "furthestsampling_cuda_launcher", "knnquery_cuda_launcher",
@@ -89,7 +106,7 @@ REFERENCE_LAUNCHERS = [
     "subtraction_forward_cuda_launcher", "subtraction_backward_cuda_launcher",
     "aggregation_forward_cuda_launcher", "aggregation_backward_cuda_launcher",
 ]
-EXPORTS = list(_SIGS) + REFERENCE_LAUNCHERS + ["tgn_version", "tgn_last_error", "tgn_launch_count", "tgn_pw_packed_bytes", "tgn_pw_struct_size", "tgn_knn_grid_bytes", "tgn_csr_bytes"]
+EXPORTS = list(_SIGS) + REFERENCE_LAUNCHERS + ["tgn_version", "tgn_last_error", "tgn_launch_count", "tgn_pw_packed_bytes", "tgn_pw_struct_size", "tgn_knn_grid_bytes", "tgn_csr_bytes", "tgn_pt_layer_struct_size"]
 
 
 class TgnError(RuntimeError):
@@ -121,8 +138,10 @@ def load() -> ctypes.CDLL:
     lib.tgn_knn_grid_bytes.restype = ctypes.c_size_t
     lib.tgn_pw_struct_size.argtypes = [_i]
     lib.tgn_pw_struct_size.restype = _i
-    if lib.tgn_pw_struct_size(0) != ctypes.sizeof(PwLayer) or lib.tgn_pw_struct_size(1) != ctypes.sizeof(PwApply):
-        raise TgnError("ctypes mirror of tgn_pw_layer_t / tgn_pw_apply_t is out of date with include/tgn_b200.h")
+    lib.tgn_pt_layer_struct_size.restype = _i
+    if (lib.tgn_pw_struct_size(0) != ctypes.sizeof(PwLayer) or lib.tgn_pw_struct_size(1) != ctypes.sizeof(PwApply)
+            or lib.tgn_pt_layer_struct_size() != ctypes.sizeof(PtLayer)):
+        raise TgnError("ctypes mirror of tgn_pw_layer_t / tgn_pw_apply_t / tgn_pt_layer_t is out of date with include/tgn_b200.h")
     _lib = lib
     return lib
 

@@ -63,7 +63,7 @@ struct PwArgs {
     tgn_pw_layer_t L;
     int nkc;                 // K chunks
     int stages;
-    uint32_t off_affine;     // float2[cin] (scale, shift) when in_affine != 0
+    uint32_t off_affine;     // float4[cin] (mean_hi, mean_lo, scale, beta) when in_affine != 0
     uint32_t off_bars;
     uint32_t smem_total;
     int n_groups;            // rows / group when extrema are produced
@@ -94,8 +94,10 @@ __device__ __forceinline__ void atomic_min_float(float* addr, float v) {
     else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// scale / shift of a BatchNorm channel from batch sums (mode 1) or running statistics (mode 2)
-__device__ __forceinline__ float2 bn_scale_shift(int mode, int c, int cn, const double* stats, double count, const float* gamma,
+// BatchNorm channel from batch sums (mode 1) or running statistics (mode 2), applied as (x - mean) * scale + beta with the mean
+// carried as hi + lo floats: folding it into a shift (x * scale + (beta - mean * scale)) costs |mean| / std ulps on the result.
+// .x = mean_hi, .y = mean_lo, .z = scale, .w = beta
+__device__ __forceinline__ float4 bn_scale_shift(int mode, int c, int cn, const double* stats, double count, const float* gamma,
                                                  const float* beta, float eps, const float* rmean, const float* rvar)
 {
     double mean, var;
@@ -106,11 +108,14 @@ __device__ __forceinline__ float2 bn_scale_shift(int mode, int c, int cn, const 
         mean = static_cast<double>(rmean[c]);
         var = static_cast<double>(rvar[c]);
     }
-    const float inv = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-    const float sc = g * inv;
-    return make_float2(sc, b - static_cast<float>(mean) * sc);
+    float4 a;
+    a.x = static_cast<float>(mean);
+    a.y = static_cast<float>(mean - static_cast<double>(a.x));
+    a.z = static_cast<float>(static_cast<double>(gamma ? gamma[c] : 1.f) / sqrt(var + static_cast<double>(eps)));
+    a.w = beta ? beta[c] : 0.f;
+    return a;
 }
+__device__ __forceinline__ float bn_apply(float x, const float4& a) { return fmaf((x - a.x) - a.y, a.z, a.w); }
 // torch's training-mode side effect: running = (1-m) running + m batch (variance unbiased)
 __device__ __forceinline__ void bn_update_running(int c, int cn, const double* stats, double count, float momentum, float* rmean, float* rvar)
 {
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_layer_kernel(const PwArgs a)
     const uint32_t bar_full = sbase + a.off_bars + 16;                 // kMaxStages x 8
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;
     const uint32_t bar_acc = bar_empty + 8 * kMaxStages;
-    float2* affine = reinterpret_cast<float2*>(smem + a.off_affine);
+    float4* affine = reinterpret_cast<float4*>(smem + a.off_affine);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + a.off_bars), "r"(kNT) : "memory");
@@ -240,8 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_layer_kernel(const PwArgs a)
                 for (int i = 0; i < kKC; ++i) {
                     const int k = k0 + i;
                     if (k < L.cin) {
-                        const float2 ss = affine[k];
-                        x[i] = fmaxf(fmaf(x[i], ss.x, ss.y), 0.f);
+                        x[i] = fmaxf(bn_apply(x[i], affine[k]), 0.f);
                     }
                 }
             }
@@ -392,21 +396,21 @@ __global__ void pw_pack_weights_kernel(int cout, int cin, int nkc, const float* 
 // out[b, c_off + c, n] = relu?(scale_c * v + shift_c), v = Y[c, b*rpb + n] or the max / min pick by sign(scale)
 __global__ void pw_apply_kernel(const tgn_pw_apply_t p)
 {
-    __shared__ float2 ss;
+    __shared__ float4 ss;
     const int c = blockIdx.y;
     if (threadIdx.x == 0) {
         ss = p.affine ? bn_scale_shift(p.affine, c, p.channels, p.stats, static_cast<double>(p.stat_rows), p.gamma, p.beta, p.eps,
                                        p.running_mean, p.running_var)
-                      : make_float2(1.f, 0.f);
+                      : make_float4(0.f, 0.f, 1.f, 0.f);
         if (p.affine == 1 && p.update_running && blockIdx.x == 0)
             bn_update_running(c, p.channels, p.stats, static_cast<double>(p.stat_rows), p.momentum, p.running_mean, p.running_var);
     }
     __syncthreads();
-    const float sc = ss.x, sh = ss.y;
-    const float* src = (p.ymin && sc < 0.f) ? p.ymin : p.src;
+    const float4 aff = ss;
+    const float* src = (p.ymin && aff.z < 0.f) ? p.ymin : p.src;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.rows; i += gridDim.x * blockDim.x) {
         const int b = i / p.rows_per_batch, n = i - b * p.rows_per_batch;
-        float v = fmaf(src[static_cast<size_t>(c) * p.rows + i], sc, sh);
+        float v = bn_apply(src[static_cast<size_t>(c) * p.rows + i], aff);
         if (p.relu) v = fmaxf(v, 0.f);
         p.out[(static_cast<size_t>(b) * p.out_channels + p.out_c_offset + c) * p.rows_per_batch + n] = v;
     }
@@ -465,7 +469,7 @@ int tgn_pw_layer_forward(const tgn_pw_layer_t* layer, void* stream)
         if (!L.extrema_atomic && (kNT / 2) % L.group != 0) { set_error("pw_layer_forward: group %d needs the atomic extrema path", L.group); return TGN_ERR_INVALID; }
     }
     a.nkc = (L.cin + kKC - 1) / kKC;
-    const uint32_t affine_bytes = L.in_affine ? static_cast<uint32_t>(L.cin) * 8 : 0;
+    const uint32_t affine_bytes = L.in_affine ? static_cast<uint32_t>(L.cin) * 16 : 0;
     int stages = kMaxStages;
     for (;; --stages) {
         a.off_affine = stages * kStageBytes;

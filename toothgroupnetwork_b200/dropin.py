@@ -63,6 +63,16 @@ def accelerate_ops_utils(ops_utils_module=None) -> None:
     crops.accelerate(ops_utils_module)
 
 
+def accelerate_blocks(blocks_module=None) -> None:
+    """Optional: run the no-grad forwards of the reference's ``PointTransformerLayer`` / ``TransitionDown``
+    (models/modules/cbl_point_transformer/blocks.py:31-44, :59-79) on the fused kernels of
+    ``toothgroupnetwork_b200.blocks_fused``; under autograd the reference's own code keeps running."""
+    from . import blocks_fused
+    if blocks_module is None:
+        blocks_module = importlib.import_module("models.modules.cbl_point_transformer.blocks")
+    blocks_fused.accelerate(blocks_module)
+
+
 def uninstall() -> None:
     for alias in _TARGETS:
         sys.modules.pop(alias, None)
