@@ -97,6 +97,14 @@ int tgn_knnquery(int b, int m, int nsample, const float *xyz, const float *new_x
  * the k-th distance, compaction, bitonic sort. */
 int tgn_crop_knn(int B, int N, int Q, int k, const float *xyz, const float *centres, void *out_idx, int idx64, void *stream);
 
+/* DBSCAN labels equal to scikit-learn's DBSCAN(eps, min_samples).fit(xyz).labels_ (float64 reduced-distance predicate, clusters
+ * numbered by their smallest core index, border points take the smallest neighbouring label, noise -1): replaces the host-side
+ * clustering of ops_utils.get_clustering_labels (ops_utils.py:98).  xyz (n,3) float32 DEVICE; workspace of
+ * tgn_dbscan_bytes(n) DEVICE bytes; labels (n) int32, core (n) bytes (1 = core sample), n_clusters DEVICE int or NULL. */
+size_t tgn_dbscan_bytes(int n);
+int tgn_dbscan(int n, const float *xyz, double eps, int min_samples, void *workspace, int *labels, unsigned char *core, int *n_clusters,
+               void *stream);
+
 /* kNN through a per-segment uniform grid: identical answers to tgn_knnquery (distinct distances: order-independent;
  * ties among the k+1 best: the query is re-run with the reference's index-order heap), ~100x fewer distance evaluations
  * on 24k-point clouds.  The grid depends only on (xyz, offset): build it once into a caller-owned DEVICE workspace of

@@ -212,8 +212,9 @@ class World:
                 importlib.import_module(name)
             if ops == "b200" and accelerate_crops:
                 # the crop search between the two stages (sklearn KDTree on the host in the reference) on the GPU too
-                from toothgroupnetwork_b200 import crops
+                from toothgroupnetwork_b200 import clustering, crops
                 crops.accelerate(sys.modules["ops_utils"])
+                clustering.accelerate(sys.modules["ops_utils"])
             if ops == "b200" and fused_blocks:
                 # no-grad forwards of PointTransformerLayer / TransitionDown on the fused kernels (autograd keeps the reference's code)
                 from toothgroupnetwork_b200 import blocks_fused

@@ -1,0 +1,124 @@
+"""The clustering step between the two stages of the reference's two-stage models, on the GPU.
+
+``ops_utils.get_clustering_labels`` (ops_utils.py:86-144, called at grouping_network_module.py:65) runs
+``sklearn.cluster.DBSCAN(eps=0.03, min_samples=30)`` on the offset-moved foreground points, splits suspiciously elongated
+clusters with MeanShift and gives every noise point the majority label of its 10 nearest labelled points (a KDTree).  On a
+trained network the DBSCAN alone costs 0.9 s per cloud on the host -- an order of magnitude more than the two networks.
+
+Here ``dbscan`` is csrc/dbscan.cu (labels and core samples equal to scikit-learn's: same float64 predicate, same cluster
+numbering, same border rule), the noise vote uses the float64 selection kernel of csrc/crop_knn.cu, and
+``get_clustering_labels`` keeps the reference's steps and return value.  The elongation test is the reference's (PCA
+eigenvalues of the core points); the MeanShift split, taken for at most three clusters and rarely, stays on scikit-learn.
+``accelerate(ops_utils_module)`` swaps the function in an imported reference ``ops_utils``.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import crops
+
+_ws = {}
+
+
+def _workspace(n: int, device) -> torch.Tensor:
+    need = int(L.load().tgn_dbscan_bytes(int(n)))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def dbscan_device(points: torch.Tensor, eps: float = 0.03, min_samples: int = 30) -> Tuple[torch.Tensor, torch.Tensor]:
+    """points (n,3) float32 CUDA -> (labels (n) int32, core (n) uint8), both on the device; equal to
+    ``sklearn.cluster.DBSCAN(eps, min_samples).fit(points)``'s ``labels_`` / ``core_sample_indices_``."""
+    L.require_cuda(points)
+    if points.dim() != 2 or points.shape[1] != 3 or points.dtype != torch.float32:
+        raise L.TgnError(f"dbscan expects (n,3) float32 points, got {tuple(points.shape)} {points.dtype}")
+    points = points.contiguous()
+    n = points.shape[0]
+    labels = torch.empty(n, dtype=torch.int32, device=points.device)
+    core = torch.empty(n, dtype=torch.uint8, device=points.device)
+    if n:
+        ws = _workspace(n, points.device)
+        L.call("tgn_dbscan", n, L.ptr(points), float(eps), int(min_samples), L.ptr(ws), L.ptr(labels), L.ptr(core), None, L.stream_ptr())
+    return labels, core
+
+
+def dbscan(points, eps: float = 0.03, min_samples: int = 30) -> Tuple[np.ndarray, np.ndarray]:
+    """numpy or tensor (n,3) -> (labels_ int64 (n), core_sample_indices_ int64) like the attributes of a fitted sklearn DBSCAN."""
+    pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float32) if isinstance(points, np.ndarray) else points, dtype=torch.float32)
+    pts = pts if pts.is_cuda else pts.cuda()
+    labels, core = dbscan_device(pts, eps, min_samples)
+    both = torch.stack([labels, core.int()]).cpu().numpy()             # one device -> host copy
+    return both[0].astype(np.int64), np.flatnonzero(both[1]).astype(np.int64)
+
+
+def _explained_variance(points: np.ndarray) -> np.ndarray:
+    """sklearn PCA(n_components=3).fit(points).explained_variance_ (ops_utils.get_eg_values :51-56): eigenvalues of the
+    sample covariance, descending."""
+    if points.shape[0] < 3:
+        return np.array([0, 0, 0])
+    x = np.asarray(points, dtype=np.float64)
+    x = x - x.mean(0)
+    ev = np.linalg.eigvalsh(x.T @ x / (x.shape[0] - 1))[::-1]
+    return np.maximum(ev, 0.0)
+
+
+def _majority(rows: np.ndarray) -> np.ndarray:
+    """per row: the most frequent value, the smallest one among equals (np.unique + argmax, ops_utils.py:139-141)."""
+    values, inv = np.unique(rows, return_inverse=True)
+    inv = inv.reshape(rows.shape)
+    counts = np.zeros((rows.shape[0], values.shape[0]), dtype=np.int32)
+    np.add.at(counts, (np.arange(rows.shape[0])[:, None], inv), 1)
+    return values[np.argmax(counts, axis=1)]
+
+
+def get_clustering_labels(moved_points, labels):
+    """Drop-in for ops_utils.get_clustering_labels (:86-144): moved_points (N,3), labels (N,) or (N,1) semantic classes ->
+    cluster label of every foreground point (labels != 0), int64."""
+    moved_points = np.asarray(moved_points)
+    cond = np.asarray(labels) != 0
+    fg = moved_points[cond, :]
+    fg_dev = torch.as_tensor(np.ascontiguousarray(fg, dtype=np.float32)).cuda()
+    lab_dev, core_dev = dbscan_device(fg_dev, 0.03, 30)
+    both = torch.stack([lab_dev, core_dev.int()]).cpu().numpy()
+    clustering_labels = both[0].astype(np.int64)
+    core_mask = both[1].astype(bool)
+    dbscan_labels = clustering_labels.copy()
+
+    uniq = [int(u) for u in np.unique(dbscan_labels) if u != -1]
+    eg_values = np.array([_explained_variance(fg[core_mask & (dbscan_labels == u), :3]) for u in uniq])
+    eg_first = eg_values[:, 0]
+    order = np.argsort(-eg_first)
+    eg_first = eg_first[order]
+    suspicious = []
+    for i in range(3):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if eg_first[i] / eg_first[3:].mean() > 8:
+                suspicious.append(order[i])
+    for idx, which in enumerate(suspicious):
+        from sklearn.cluster import MeanShift                      # host-side, rare: at most three elongated clusters
+        # the reference indexes its list of clusters by position and then rewrites the label equal to that position (:128-132)
+        members = fg[dbscan_labels == uniq[which], :3].astype(np.float64)
+        split = MeanShift(bandwidth=0.07).fit(members)
+        clustering_labels[clustering_labels == which] = split.labels_ + 100 * (idx + 1)
+
+    noise = clustering_labels == -1
+    if noise.any():          # (with no noise at all the reference raises ValueError from KDTree.query on an empty array, :135)
+        keep = ~noise
+        if int(keep.sum()) < 10:
+            raise ValueError("k must be less than or equal to the number of training points")
+        near = crops.nearest_neighbor_crops(fg_dev[torch.as_tensor(keep).cuda()].unsqueeze(0), fg_dev[torch.as_tensor(noise).cuda()].unsqueeze(0), 10)[0]
+        clustering_labels[noise] = _majority(clustering_labels[keep][near.cpu().numpy()])
+    return clustering_labels
+
+
+def accelerate(ops_utils_module) -> None:
+    """Swap ops_utils.get_clustering_labels of an imported reference module for the device version."""
+    ops_utils_module.get_clustering_labels = get_clustering_labels

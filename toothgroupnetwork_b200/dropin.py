@@ -57,10 +57,11 @@ def accelerate_ops_utils(ops_utils_module=None) -> None:
     """Optional: also replace the host-side crop search of the reference's ``ops_utils`` (sklearn KDTree.query(k=3072),
     ops_utils.py:146-161, and the gather :198-218) with the GPU versions of ``toothgroupnetwork_b200.crops``.  Call after
     ``install()``; imports ``ops_utils`` from ``sys.path`` when no module is passed."""
-    from . import crops
+    from . import clustering, crops
     if ops_utils_module is None:
         ops_utils_module = importlib.import_module("ops_utils")
     crops.accelerate(ops_utils_module)
+    clustering.accelerate(ops_utils_module)        # DBSCAN + noise vote of get_clustering_labels (ops_utils.py:86-144)
 
 
 def accelerate_blocks(blocks_module=None) -> None:
