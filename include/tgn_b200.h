@@ -290,6 +290,8 @@ typedef struct {
 } tgn_pt_layer_t;
 int tgn_pt_layer_forward(const tgn_pt_layer_t *layer, void *stream);
 int tgn_pt_layer_struct_size(void);
+/* layers with fewer queries than this run one CTA per query instead of one warp per query (default 1024); returns the old value */
+int tgn_pt_layer_set_cta_threshold(int n_queries);
 
 size_t tgn_pw_packed_bytes(int cout, int cin);
 int tgn_pw_struct_size(int which);         /* sizeof(tgn_pw_layer_t) (0) / sizeof(tgn_pw_apply_t) (1): binding self-check */

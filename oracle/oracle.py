@@ -408,3 +408,95 @@ def sa_group_mlp_max_batch(xyz, feats, new_xyz, gidx, layers: Sequence[MlpParams
     lib().oracle_sa_group_mlp_max_batch(B, N, S, K, D, _p(xyz, _f32p), None if f is None else _p(f, _f32p), _p(new_xyz, _f32p),
                                         _p(gidx, _i64p), len(layers), chv, arr(wts), arr(scs), arr(shs), _p(out, _f32p))
     return out
+
+
+# ----------------------------------------------------------------------------- point-transformer blocks
+def _bn_rows(y: torch.Tensor, bn: dict, prefix: str, train_bn: bool, eps: float = 1e-5) -> torch.Tensor:
+    """BatchNorm1d over a (n, K, c) tensor the way blocks.py applies it: transposed to (n, c, K), i.e. statistics per
+    channel over all n * K rows (blocks.py:38,40,72)."""
+    if train_bn:
+        mu = y.mean(dim=(0, 1))
+        var = y.var(dim=(0, 1), unbiased=False)
+    else:
+        mu, var = bn[prefix + ".running_mean"].to(y.dtype), bn[prefix + ".running_var"].to(y.dtype)
+    return (y - mu) / torch.sqrt(var + eps) * bn[prefix + ".weight"].to(y.dtype) + bn[prefix + ".bias"].to(y.dtype)
+
+
+def point_transformer_layer(p, x, o, state: dict, nsample: int, share_planes: int = 8, train_bn: bool = True, dtype=torch.float32):
+    """blocks.PointTransformerLayer.forward (models/modules/cbl_point_transformer/blocks.py:31-44) as a pure function of the
+    layer's ``state_dict``: p (n,3), x (n,c_in), o (b) -> (n, c).  kNN through the oracle's knnquery on the float32
+    coordinates; everything after the gathers in ``dtype`` (float64 = the exact answer for the same neighbours)."""
+    p32 = np.ascontiguousarray(p.detach().cpu().numpy(), dtype=np.float32)
+    off = np.ascontiguousarray(o.detach().cpu().numpy(), dtype=np.int32)
+    idx, _, _ = knnquery(int(nsample), p32, p32, off, off)
+    idx = torch.from_numpy(np.ascontiguousarray(idx)).long()
+    S = {k: v.detach().cpu().to(dtype) if v.is_floating_point() else v for k, v in state.items()}
+    p, x = p.detach().cpu().to(dtype), x.detach().cpu().to(dtype)
+    lin = lambda t, name: t @ S[name + ".weight"].t() + S[name + ".bias"]
+    x_q, x_k, x_v = lin(x, "linear_q"), lin(x, "linear_k"), lin(x, "linear_v")                   # :33
+    n, K = idx.shape
+    p_r = p[idx.view(-1)].view(n, K, 3) - p.unsqueeze(1)                                         # queryandgroup use_xyz (:34,36)
+    g_k, g_v = x_k[idx.view(-1)].view(n, K, -1), x_v[idx.view(-1)].view(n, K, -1)                # :34-35
+    t = lin(p_r, "linear_p.0")                                                                   # :38  Linear(3,3)
+    t = F.relu(_bn_rows(t, S, "linear_p.1", train_bn))
+    p_r = lin(t, "linear_p.3")                                                                   # Linear(3,c)
+    w = g_k - x_q.unsqueeze(1) + p_r                                                             # :39 (out_planes == mid_planes)
+    w = F.relu(_bn_rows(w, S, "linear_w.0", train_bn))                                           # :40
+    w = lin(w, "linear_w.2")
+    w = F.relu(_bn_rows(w, S, "linear_w.3", train_bn))
+    w = lin(w, "linear_w.5")
+    w = torch.softmax(w, dim=1)                                                                  # :41 over the K neighbours
+    c, s = g_v.shape[2], share_planes
+    return ((g_v + p_r).view(n, K, s, c // s) * w.unsqueeze(2)).sum(1).view(n, c)                # :43
+
+
+def transition_down(p, x, o, state: dict, stride: int, nsample: int, train_bn: bool = True, dtype=torch.float32):
+    """blocks.TransitionDown.forward with stride != 1 (blocks.py:62-74): FPS to n // stride points per cloud, kNN grouping of
+    [xyz_rel | feats], Linear (no bias) + BatchNorm + ReLU, max over the K neighbours -> (new_p, new_x, new_o)."""
+    p32 = np.ascontiguousarray(p.detach().cpu().numpy(), dtype=np.float32)
+    off = np.ascontiguousarray(o.detach().cpu().numpy(), dtype=np.int32)
+    counts = np.diff(np.concatenate([[0], off])) // stride
+    n_o = np.cumsum(counts).astype(np.int32)                                                     # :64-68
+    sel = furthestsampling(p32, off, n_o)                                                        # :69
+    n_p = p32[sel]
+    idx, _, _ = knnquery(int(nsample), p32, n_p, off, n_o)                                       # :71
+    idx = torch.from_numpy(np.ascontiguousarray(idx)).long()
+    S = {k: v.detach().cpu().to(dtype) if v.is_floating_point() else v for k, v in state.items()}
+    pd, xd, npd = p.detach().cpu().to(dtype), x.detach().cpu().to(dtype), torch.from_numpy(n_p).to(dtype)
+    m, K = idx.shape
+    g = torch.cat([pd[idx.view(-1)].view(m, K, 3) - npd.unsqueeze(1), xd[idx.view(-1)].view(m, K, -1)], -1)
+    y = g @ S["linear.weight"].t()                                                               # :72
+    y = F.relu(_bn_rows(y, S, "bn", train_bn))
+    return torch.from_numpy(n_p), y.max(dim=1).values, torch.from_numpy(n_o)                     # :73 MaxPool1d(nsample)
+
+
+# ----------------------------------------------------------------------------- clustering (SURVEY 8(f)-4)
+def dbscan(points, eps: float = 0.03, min_samples: int = 30) -> Tuple[np.ndarray, np.ndarray]:
+    """scikit-learn's DBSCAN(eps, min_samples).fit(points) -> (labels_, core_sample_indices_), the call of
+    ops_utils.get_clustering_labels (ops_utils.py:98).  scikit-learn is a dependency of the reference that is not vendored in
+    its tree (no version pinned there; this image has 1.9.0); its published algorithm, restated:
+    sklearn/cluster/_dbscan.py -- neighbourhoods = radius_neighbors(eps) over a KDTree of the float64 copy of the points
+    (reduced distance (dx^2 + dy^2) + dz^2 <= eps^2, the point itself included), core = at least min_samples neighbours;
+    sklearn/cluster/_dbscan_inner.pyx -- visit points in index order, flood each unlabelled core point's component with a
+    stack (non-core points are labelled but not expanded), label numbers in visiting order, the rest stays -1.
+    Brute force, for test sizes."""
+    x = np.asarray(points, dtype=np.float64)
+    n = x.shape[0]
+    d = x[:, None, :] - x[None, :, :]
+    within = ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]) <= eps * eps
+    core = within.sum(1) >= min_samples
+    labels = np.full(n, -1, dtype=np.int64)
+    label = 0
+    for i in range(n):
+        if labels[i] != -1 or not core[i]:
+            continue
+        stack = [i]
+        while stack:
+            v = stack.pop()
+            if labels[v] != -1:
+                continue
+            labels[v] = label
+            if core[v]:
+                stack.extend(int(u) for u in np.flatnonzero(within[v]) if labels[u] == -1)
+        label += 1
+    return labels, np.flatnonzero(core).astype(np.int64)

@@ -56,6 +56,18 @@ def test_dbscan_equals_sklearn_with_noise_borders_and_duplicates(seed):
     check_against_sklearn(pts, eps=0.011, min_samples=3)
 
 
+@pytest.mark.parametrize("name", ["blobs", "blobs_loose", "arch"])
+def test_dbscan_equals_the_sklearn_fixture_and_the_oracle(name):
+    """no scikit-learn needed at run time: tests/golden/ref_sklearn_dbscan.npz + the oracle's restatement"""
+    from oracle import oracle as O
+    fix = np.load(os.path.join(ROOT, "tests", "golden", "ref_sklearn_dbscan.npz"))
+    pts, eps, ms = fix[name + "_points"], float(fix[name + "_eps"]), int(fix[name + "_min_samples"])
+    labels, core = clustering.dbscan(pts, eps, ms)
+    assert np.array_equal(labels, fix[name + "_labels"]) and np.array_equal(core, fix[name + "_core"])
+    o_labels, o_core = O.dbscan(pts, eps, ms)
+    assert np.array_equal(labels, o_labels) and np.array_equal(core, o_core)
+
+
 def test_dbscan_small_and_degenerate_inputs():
     for pts in (np.zeros((0, 3), np.float32), np.zeros((1, 3), np.float32), np.zeros((40, 3), np.float32),
                 np.linspace(0, 100, 90, dtype=np.float32).reshape(30, 3)):

@@ -22,6 +22,7 @@ _SIGS = {
     "tgn_furthestsampling": [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tgn_knnquery": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tgn_crop_knn": [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "tgn_pt_layer_set_cta_threshold": [_i],
     "tgn_dbscan": [_i, _vp, ctypes.c_double, _i, _vp, _vp, _vp, _vp, _vp],
     "tgn_csr_build": [ctypes.c_longlong, _i, _vp, _vp, _vp],
     "tgn_gather_backward_det": [ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp],

@@ -61,7 +61,11 @@ __device__ __forceinline__ float bn_relu(float x, const BnAffine& a)
     return fmaxf(fmaf((x - a.mean_hi) - a.mean_lo, a.scale, a.beta), 0.f);
 }
 
-template <int CPL, int PASS>
+// CTAQ = false: one warp per query (shallow levels: tens of thousands of queries).
+// CTAQ = true : one CTA per query, its warps take the neighbours round-robin and meet in shared memory for the softmax and the
+//               output sum (deep levels: a few hundred queries of 128-512 channels, where a single warp walking K neighbours
+//               times c/8 x c products is pure latency).
+template <int CPL, int PASS, bool CTAQ>
 __global__ void __launch_bounds__(kWarps * 32) pt_layer_kernel(const tgn_pt_layer_t L)
 {
     constexpr int C = 32 * CPL, CS = 4 * CPL;                  // channels, channels / share_planes (= 8)
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(kWarps * 32) pt_layer_kernel(const tgn_pt_laye
     BnAffine* ss_a = reinterpret_cast<BnAffine*>(dyn);         // [C]   BatchNorm_a mean / scale / beta
     BnAffine* ss_b = ss_a + C;                                 // [CS]  BatchNorm_b
     BnAffine* ss_p = ss_b + CS;                                // [4]   BatchNorm_p (3 used)
-    float* logits_all = reinterpret_cast<float*>(ss_p + 4);    // [kWarps][K][CS]
+    float* logits_all = reinterpret_cast<float*>(ss_p + 4);    // [kWarps][K][CS]; CTAQ: [K][CS] then [kWarps][C] output partials
     __shared__ double red[kWarps][8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -81,7 +85,9 @@ __global__ void __launch_bounds__(kWarps * 32) pt_layer_kernel(const tgn_pt_laye
     if (PASS >= 3) for (int m = tid; m < CS; m += kWarps * 32)
         ss_b[m] = scale_shift(L.bn_mode[2], m, CS, L.stats_b, cnt, L.b_gamma, L.b_beta, L.b_eps, L.b_rmean, L.b_rvar);
     __syncthreads();
-    float* logits = logits_all + static_cast<size_t>(warp) * L.K * CS;
+    float* logits = CTAQ ? logits_all : logits_all + static_cast<size_t>(warp) * L.K * CS;
+    float* out_part = logits_all + static_cast<size_t>(L.K) * CS;           // CTAQ only
+    const int j0 = CTAQ ? warp : 0, jstep = CTAQ ? kWarps : 1;
 
     // small parameters of linear_p into registers
     float w0m[9], b0v[3];
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(kWarps * 32) pt_layer_kernel(const tgn_pt_laye
         for (int q = 0; q < (CS + 31) / 32; ++q) { sb1[q] = 0.0; sb2[q] = 0.0; }
     }
 
-    for (int i = blockIdx.x * kWarps + warp; i < L.n; i += gridDim.x * kWarps) {
+    for (int i = CTAQ ? blockIdx.x : blockIdx.x * kWarps + warp; i < L.n; i += CTAQ ? gridDim.x : gridDim.x * kWarps) {
         const float pix = __ldg(L.p + 3 * static_cast<size_t>(i)), piy = __ldg(L.p + 3 * static_cast<size_t>(i) + 1),
                     piz = __ldg(L.p + 3 * static_cast<size_t>(i) + 2);
         float xq[CPL];
@@ -129,19 +135,19 @@ __global__ void __launch_bounds__(kWarps * 32) pt_layer_kernel(const tgn_pt_laye
         for (int phase = 0; phase < (PASS == 3 ? 2 : 1); ++phase) {
             if (PASS == 3 && phase == 1) {
                 // softmax over the K neighbours, one column m per lane (strided), in place (nn.Softmax(dim=1), blocks.py:40)
-                __syncwarp();
-                for (int m = lane; m < CS; m += 32) {
+                if (CTAQ) __syncthreads(); else __syncwarp();
+                for (int m = CTAQ ? tid : lane; m < CS; m += CTAQ ? kWarps * 32 : 32) {
                     float mx = -INFINITY;
                     for (int j = 0; j < L.K; ++j) mx = fmaxf(mx, logits[j * CS + m]);
                     float sum = 0.f;
                     for (int j = 0; j < L.K; ++j) { const float e = expf(logits[j * CS + m] - mx); logits[j * CS + m] = e; sum += e; }
                     for (int j = 0; j < L.K; ++j) logits[j * CS + m] = logits[j * CS + m] / sum;
                 }
-                __syncwarp();
+                if (CTAQ) __syncthreads(); else __syncwarp();
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) out[q] = 0.f;
             }
-            for (int j = 0; j < L.K; ++j) {
+            for (int j = j0; j < L.K; j += jstep) {
                 const int nbr = __ldg(L.idx + static_cast<size_t>(i) * L.K + j);
                 const float rx = __ldg(L.p + 3 * static_cast<size_t>(nbr)) - pix, ry = __ldg(L.p + 3 * static_cast<size_t>(nbr) + 1) - piy,
                             rz = __ldg(L.p + 3 * static_cast<size_t>(nbr) + 2) - piz;
@@ -214,11 +220,24 @@ __global__ void __launch_bounds__(kWarps * 32) pt_layer_kernel(const tgn_pt_laye
 #pragma unroll
             for (int q = 0; q < CPL; ++q) { acc1[q] += f1[q]; acc2[q] += f2[q]; }
         }
-        if (PASS == 3) {
+        if (PASS == 3 && !CTAQ) {
 #pragma unroll
             for (int q = 0; q < CPL; ++q) L.out[static_cast<size_t>(i) * C + 32 * q + lane] = out[q];
         }
+        if (PASS == 3 && CTAQ) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) out_part[warp * C + 32 * q + lane] = out[q];
+            __syncthreads();
+            for (int ch = tid; ch < C; ch += kWarps * 32) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) sum += out_part[w * C + ch];
+                L.out[static_cast<size_t>(i) * C + ch] = sum;
+            }
+            __syncthreads();                                       // logits / partials are reused by the next query
+        }
     }
+    if (PASS == 1 || PASS == 2) __syncthreads();                   // the statistics below reuse the logits area
 
     // ---- statistics: CTA reduction, two fp64 atomics per channel per CTA --------------------------------------------------
     if (PASS == 0) {
@@ -282,17 +301,28 @@ __global__ void pt_update_running_kernel(const tgn_pt_layer_t L)
     }
 }
 
+template <int CPL, int PASS, bool CTAQ>
+int launch_pass_as(const tgn_pt_layer_t& L, cudaStream_t st)
+{
+    constexpr int C = 32 * CPL, CS = 4 * CPL;
+    const size_t head = (C + CS + 4) * sizeof(BnAffine);
+    size_t smem = head + static_cast<size_t>(kWarps) * L.K * CS * sizeof(float);
+    smem = std::max(smem, head + static_cast<size_t>(kWarps) * 2 * C * sizeof(double));
+    smem = std::max(smem, head + (static_cast<size_t>(L.K) * CS + static_cast<size_t>(kWarps) * C) * sizeof(float));
+    const int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(pt_layer_kernel<CPL, PASS, CTAQ>), smem);
+    if (rc != TGN_OK) return rc;
+    const int grid = CTAQ ? std::max(1, std::min(L.n, 8 * sm_count())) : std::max(1, std::min((L.n + kWarps - 1) / kWarps, 4 * sm_count()));
+    pt_layer_kernel<CPL, PASS, CTAQ><<<grid, kWarps * 32, smem, st>>>(L);
+    return check_launch("pt_layer_kernel");
+}
+
+// queries below this count get a CTA each (0 = never, INT_MAX = always: tgn_pt_layer_set_cta_threshold, for measurements)
+int g_cta_threshold = 1024;
+
 template <int CPL, int PASS>
 int launch_pass(const tgn_pt_layer_t& L, cudaStream_t st)
 {
-    constexpr int C = 32 * CPL, CS = 4 * CPL;
-    size_t smem = (C + CS + 4) * sizeof(BnAffine) + static_cast<size_t>(kWarps) * L.K * CS * sizeof(float);
-    smem = std::max(smem, (C + CS + 4) * sizeof(BnAffine) + static_cast<size_t>(kWarps) * 2 * C * sizeof(double));
-    const int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(pt_layer_kernel<CPL, PASS>), smem);
-    if (rc != TGN_OK) return rc;
-    const int grid = std::max(1, std::min((L.n + kWarps - 1) / kWarps, 4 * sm_count()));
-    pt_layer_kernel<CPL, PASS><<<grid, kWarps * 32, smem, st>>>(L);
-    return check_launch("pt_layer_kernel");
+    return L.n < g_cta_threshold ? launch_pass_as<CPL, PASS, true>(L, st) : launch_pass_as<CPL, PASS, false>(L, st);
 }
 
 template <int CPL>
@@ -316,6 +346,13 @@ int run_layer(const tgn_pt_layer_t& L, cudaStream_t st)
 extern "C" {
 
 int tgn_pt_layer_struct_size(void) { return static_cast<int>(sizeof(tgn_pt_layer_t)); }
+
+int tgn_pt_layer_set_cta_threshold(int n_queries)
+{
+    const int old = tgn::g_cta_threshold;
+    tgn::g_cta_threshold = n_queries;
+    return old;
+}
 
 int tgn_pt_layer_forward(const tgn_pt_layer_t* layer, void* stream)
 {
