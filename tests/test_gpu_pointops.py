@@ -37,6 +37,7 @@ FPS_CASES = [
     ("crops16x3072", lambda: [clouds.dental_arch(3072, 10 + i)[0] for i in range(16)], [768] * 16),
     ("more_samples_than_unique", lambda: [clouds.with_duplicates(clouds.cube(40, 9), 9)], [80]),
     ("raw_mesh_100k", lambda: [clouds.dental_arch(100000, 12)[0]], [1500]),                 # SURVEY 8(f) next-2 size
+    ("raw_mesh_200k", lambda: [clouds.dental_arch(200000, 15)[0]], [1200]),                # 3125 buckets: 7 per lane at 16 warps
     ("flat_and_tiny_extent", lambda: [clouds.cube(9000, 13) * torch.tensor([1.0, 1e-3, 0.0])], [700]),  # degenerate bbox
     ("arch_dups_24k", lambda: [clouds.with_duplicates(clouds.dental_arch(12000, 14)[0], 14)], [2048]),
 ]

@@ -698,7 +698,7 @@ fps_bucket_kernel2(const float* __restrict__ xyz, const int* __restrict__ offset
 // never leave registers -- box tests need no shared-memory loads, an update hands the new candidate to the owner lane with
 // three shuffles, the warp's candidate is two CREDUX over registers and the winning lane publishes its slot directly.
 template <int MT_, int BPL>
-__global__ void __launch_bounds__(MT_, 1024 / MT_ > 2 ? 2 : 1024 / MT_)
+__global__ void __launch_bounds__(MT_, (MT_ == 512 && BPL >= 3) ? 1 : (1024 / MT_ > 2 ? 2 : 1024 / MT_))     // raw-mesh shapes: one CTA per SM, 128 registers
 fps_bucket_kernel3(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                    float* tmp, int* __restrict__ idx, BucketWs ws, int bs_log2)
 {
@@ -909,7 +909,9 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
         // the single-barrier kernel with register-resident tables at 16 warps per cloud wins (1.02 ms against 1.62 ms per call
         // up to one cloud per SM, 3.16 against 3.32 at four); beyond that the batch is DRAM-bound and the three-barrier kernel
         // at 4 warps per cloud, 8 clouds per SM, stays ahead (5.27 against 6.17 ms per 1184 clouds).
-        if (shape == 0 && b <= 4 * sms && ws.nbmax <= 2 * 512) shape = 200 + 16;
+        // Raw meshes (one cloud of 1e5..2e5 vertices -> 24 000, gen_utils.py:135-140): the same kernel with 4-8 buckets per lane
+        // while every cloud can have an SM to itself (profiles/r2_raw_mesh_fps.json).
+        if (shape == 0 && ((b <= 4 * sms && ws.nbmax <= 2 * 512) || (b <= sms && ws.nbmax <= 8 * 512))) shape = 200 + 16;
         const bool v2 = shape >= 100 && shape < 200;          // 100 + W: the single-barrier schedule (fps_bucket_kernel2)
         const bool v3 = shape >= 200;                         // 200 + W: the same with register-resident bucket tables (fps_bucket_kernel3)
         int warps = shape % 100;
@@ -920,6 +922,9 @@ int fps_bucket_launch(int b, int n_max, const float* xyz, const int* offset, con
             if (warps == 32 && bpl <= 1) rc = launch_main3<1024, 1>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
             else if (warps == 16 && bpl <= 1) rc = launch_main3<512, 1>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
             else if (warps == 16 && bpl <= 2) rc = launch_main3<512, 2>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
+            else if (warps == 16 && bpl <= 4) rc = launch_main3<512, 4>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);     // <= 131 072 points
+            else if (warps == 16 && bpl <= 6) rc = launch_main3<512, 6>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);     // <= 196 608
+            else if (warps == 16 && bpl <= 8) rc = launch_main3<512, 8>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);     // <= kMaxBuckets
             else if (warps == 8 && bpl <= 1) rc = launch_main3<256, 1>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
             else if (warps == 8 && bpl <= 2) rc = launch_main3<256, 2>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
             else if (warps == 8 && bpl <= 4) rc = launch_main3<256, 4>(b, xyz, offset, new_offset, tmp, idx, ws, bs_log2, stream);
