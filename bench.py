@@ -475,6 +475,18 @@ def extras(device) -> dict:
             out["latency_ms"]["sa1_step"] = [{k: r[k] for k in ("clouds", "ours_ms", "ref_gpu_ms", "speedup")} for r in out["ref_gpu"]["runs"]]
         else:
             out["ref_gpu"] = {"unavailable": "oracle/_ref (reference kernels / python snapshot) not present on this box"}
+        # SURVEY 8(f) rows built after the hot path: each leg is independent and may not take the bench line down with it
+        nxt = {}
+        for name, leg in (("raw_mesh_fps_100k_to_24k", op_bench.raw_mesh_fps), ("dbscan_moved_foreground", op_bench.dbscan_row),
+                          ("tgnet_fps_nograd_forward", op_bench.tgnet_nograd_row)):
+            if name == "tgnet_fps_nograd_forward" and not (op_bench.ref_available() and op_bench.ref_models_available()):
+                nxt[name] = {"unavailable": "reference python snapshot not present on this box"}
+                continue
+            try:
+                nxt[name] = leg()
+            except Exception as e:                                   # noqa: BLE001 -- reported, not hidden
+                nxt[name] = {"error": repr(e)[:300]}
+        out["next_rows"] = nxt
     return out
 
 

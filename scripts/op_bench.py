@@ -281,3 +281,79 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8(f) rows
+def raw_mesh_fps(n=100000, m=24000):
+    """8(f)-2: one raw mesh of n vertices -> m samples (gen_utils.py:135-140), beside the verbatim reference kernel, bitwise."""
+    from toothgroupnetwork_b200 import clouds, pointops
+    xyz = clouds.dental_arch(n, 7)[0].cuda().contiguous()
+    off, noff = torch.tensor([n], dtype=torch.int32).cuda(), torch.tensor([m], dtype=torch.int32).cuda()
+    got = pointops.fps_packed(xyz, off, noff, n, m)
+    row = {"n": n, "m": m, "ours_ms": time_ms(lambda: pointops.fps_packed(xyz, off, noff, n, m), warm=1, reps=3)}
+    if ref_available():
+        from oracle import ref_cuda
+        ridx, _ = ref_cuda.furthestsampling(xyz, off, noff, n, m)
+        row["idx_bitwise_vs_reference_kernel"] = bool(torch.equal(ridx, got))
+        row["ref_kernel_ms"] = time_ms(lambda: ref_cuda.furthestsampling(xyz, off, noff, n, m), warm=0, reps=2)
+        row["speedup"] = row["ref_kernel_ms"] / row["ours_ms"]
+    return row
+
+
+def dbscan_row(pull=0.9, jitter=0.004, n=24000):
+    """8(f)-4: DBSCAN(eps=0.03, min_samples=30) of ops_utils.get_clustering_labels (:98) on offset-moved foreground points:
+    scikit-learn on the host (what the reference runs) beside csrc/dbscan.cu; labels and core samples compared."""
+    import time
+    from toothgroupnetwork_b200 import clouds, clustering
+    xyz, _, label = clouds.dental_arch(n, 0)
+    xyz, label = xyz.numpy(), np.where(label.numpy() < 0, 0, label.numpy()).astype(np.int64)
+    cent = np.stack([xyz[label == c].mean(0) if (label == c).any() else np.zeros(3, np.float32) for c in range(int(label.max()) + 1)])
+    fg = (xyz + pull * (cent[label] - xyz) + np.random.default_rng(0).normal(0, jitter, xyz.shape)).astype(np.float32)[label != 0]
+    dev = torch.as_tensor(fg).cuda()
+    lab, core = clustering.dbscan(fg)
+    row = {"points": int(len(fg)), "pull": pull, "device_ms_resident": time_ms(lambda: clustering.dbscan_device(dev)),
+           "device_ms_numpy_in_out": time_ms(lambda: clustering.dbscan(fg))}
+    try:
+        from sklearn.cluster import DBSCAN
+        t = time.perf_counter()
+        ref = DBSCAN(eps=0.03, min_samples=30).fit(fg)
+        row["sklearn_host_ms"] = (time.perf_counter() - t) * 1e3
+        row["labels_equal"] = bool(np.array_equal(lab, ref.labels_) and np.array_equal(core, ref.core_sample_indices_))
+        row["speedup"] = row["sklearn_host_ms"] / row["device_ms_numpy_in_out"]
+    except ImportError:
+        row["sklearn_host_ms"] = None
+    return row
+
+
+def tgnet_nograd_row(points=24000):
+    """8(f)-3 in context: GroupingNetworkModule (tgnet_fps) forward under no_grad on the reference's unmodified model files: reference
+    operators / this package with the reference's block code / this package with the fused blocks, train-mode BatchNorm."""
+    import model_parity as mp
+    from oracle import ref_models
+    from toothgroupnetwork_b200 import blocks_fused
+    feats, labels = mp.make_inputs(points)
+    ms, outs, state = {}, {}, None
+    for ops in ("reference", "b200"):
+        w = ref_models.World(ops)
+        with w, torch.no_grad():
+            torch.manual_seed(0)
+            module = w.mod("models.modules.grouping_network_module").GroupingNetworkModule({"model_parameter": dict(mp.TGN_PARAMS)}).cuda().train()
+            if state is None:
+                state = {k: v.clone() for k, v in module.state_dict().items()}
+
+            def fwd():
+                module.load_state_dict(state)
+                return module([feats, labels])
+
+            outs[ops] = fwd()["sem_1"].clone()
+            ms[ops] = time_ms(fwd, warm=1, reps=3)
+            if ops == "b200":
+                blocks_fused.set_enabled(False)
+                try:
+                    ms["b200_unfused_blocks"] = time_ms(fwd, warm=1, reps=3)
+                finally:
+                    blocks_fused.set_enabled(True)
+    a, b = outs["b200"].double(), outs["reference"].double()
+    err = float(((a - b).abs() / b.abs().clamp(min=0.05 * float(b.abs().max()))).max())
+    return {"points": points, "ms": ms, "speedup_vs_reference_ops": ms["reference"] / ms["b200"], "sem_1_elementwise_vs_reference": err,
+            "note": "train-mode BatchNorm amplifies fp32 rounding for both sides; profiles/r2_model_parity_tgnet_nograd.json holds the float64 verdict"}

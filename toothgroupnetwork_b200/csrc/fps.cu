@@ -226,7 +226,9 @@ fps_resident_kernel(const float* __restrict__ xyz, const int* __restrict__ offse
                 const int src = __ffs(__ballot_sync(FULL, cv == cmax && ck == ckey)) - 1;
                 const int jw = __shfl_sync(FULL, cj, src);
                 if (lane == 0) {
-                    const float* pw = xyz + 3 * (static_cast<size_t>(start_n[g]) + jw);
+                    // a CTA whose slice of a tiny cloud holds only pads publishes a losing candidate (value -1) whose index lies
+                    // past the cloud: its coordinates are never used, but the read must stay inside the cloud
+                    const float* pw = xyz + 3 * (static_cast<size_t>(start_n[g]) + (jw < n[g] ? jw : 0));
                     const float wx = __ldg(pw), wy = __ldg(pw + 1), wz = __ldg(pw + 2);
                     uint32_t* slot = &mailbox[g][par][rank * kCandWords];
                     if (CS > 1) {
