@@ -152,11 +152,43 @@ def test_dropin_serves_the_reference_real_model_files():
         assert count(g) == 15729246
         # the crop search of ops_utils is served by the GPU version too
         assert w.mod("ops_utils").get_nearest_neighbor_idx.__module__ == "toothgroupnetwork_b200.crops"
+        # ... and so are the clustering between the stages and the no-grad forwards of the transformer blocks
+        assert w.mod("ops_utils").get_clustering_labels.__module__ == "toothgroupnetwork_b200.clustering"
+        assert blocks.PointTransformerLayer._tgn_fused and blocks.PointTransformerLayer.forward.__name__ == "ptl_forward"
+        assert blocks.TransitionDown.forward.__name__ == "td_forward"
     # state_dict keys are the reference's (checkpoints load unchanged)
     ref = ref_models.World("reference", cpu_dry_run=True)
     with ref:
         want = set(ref.mod("models.modules.pointnet_pp").get_model().state_dict().keys())
     assert set(pp.state_dict().keys()) == want
+
+
+def test_fused_blocks_step_aside_without_a_gpu_or_under_autograd():
+    """blocks_fused only takes CUDA fp32 inputs of supported shapes when no gradient is needed; everything else is the reference's code."""
+    import torch
+    import torch.nn as nn
+    from toothgroupnetwork_b200 import blocks_fused
+
+    class Layer(nn.Module):                                           # attribute layout of blocks.PointTransformerLayer (:15-29)
+        def __init__(self, c, share=8):
+            super().__init__()
+            self.mid_planes = self.out_planes = c
+            self.share_planes, self.nsample = share, 16
+            self.linear_q = nn.Linear(c, c)
+            self.linear_p = nn.Sequential(nn.Linear(3, 3), nn.BatchNorm1d(3), nn.ReLU(), nn.Linear(3, c))
+            self.linear_w = nn.Sequential(nn.BatchNorm1d(c), nn.ReLU(), nn.Linear(c, c // share), nn.BatchNorm1d(c // share), nn.ReLU(),
+                                          nn.Linear(c // share, c // share))
+
+    p, x, o = torch.randn(50, 3), torch.randn(50, 32), torch.tensor([50], dtype=torch.int32)
+    with torch.no_grad():
+        assert not blocks_fused.pt_layer_fusable(Layer(32), p, x, o)                      # CPU tensors
+    td = nn.Module()
+    td.stride, td.nsample, td.linear, td.bn = 4, 16, nn.Linear(35, 64, bias=False), nn.BatchNorm1d(64)
+    with torch.no_grad():
+        assert not blocks_fused.transition_down_fusable(td, p, x, o)
+    assert blocks_fused._needs_grad(Layer(32), p, x) and not blocks_fused._needs_grad(Layer(32).requires_grad_(False), p, x)
+    bn = nn.BatchNorm1d(4, momentum=None)                              # cumulative moving average: not a shape the kernels update
+    assert not blocks_fused._bn_ok(bn) and blocks_fused._bn_ok(nn.BatchNorm1d(4)) and blocks_fused._bn_mode(nn.BatchNorm1d(4).eval()) == 2
 
 
 def test_square_distance_matches_oracle_bitwise_on_cpu():
