@@ -14,6 +14,7 @@ of which three are cuDNN BatchNorms over (n, c, K) views -- 56 % of the kernel t
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import torch
 
@@ -103,7 +104,7 @@ def transition_down_fusable(td, p, x, o) -> bool:
     return _bn_ok(td.bn) and td.linear.bias is None and pn2._pw_enabled
 
 
-_td_chains = {}
+_td_chains = weakref.WeakKeyDictionary()          # module -> its packed-weight chain; entries go with the module
 
 
 def transition_down_forward(td, pxo):
@@ -123,7 +124,9 @@ def transition_down_forward(td, pxo):
     n_p = p[idx.long(), :]
     gidx, _ = pointops.knn_packed(int(td.nsample), p, n_p, o, n_o)              # (m, K) global row ids
     m, K = gidx.shape
-    chain = _td_chains.setdefault(id(td), pn2._PwChain())
+    chain = _td_chains.get(td)
+    if chain is None:
+        chain = _td_chains[td] = pn2._PwChain()
     out = torch.empty((1, td.linear.out_features, m), dtype=torch.float32, device=x.device)
     pn2._pw_set_abstraction(chain, [td.linear], [td.bn], p.view(1, -1, 3), x.contiguous().view(1, x.shape[0], -1), n_p.view(1, m, 3),
                             gidx.view(1, m, K), True, out, 0)
