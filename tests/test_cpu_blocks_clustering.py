@@ -64,3 +64,8 @@ def test_clustering_host_helpers():
     from sklearn.decomposition import PCA
     assert np.allclose(clustering._explained_variance(x), PCA(n_components=3).fit(x).explained_variance_, rtol=1e-10)
     assert np.array_equal(clustering._explained_variance(x[:2]), np.array([0, 0, 0]))
+    # float64 input is taken when it holds float32 values, refused otherwise (it would be clustered on rounded coordinates)
+    f32 = np.random.default_rng(1).normal(size=(20, 3)).astype(np.float32)
+    assert clustering._as_float32(f32.astype(np.float64)).dtype == np.float32
+    with pytest.raises(clustering.L.TgnError):
+        clustering._as_float32(f32.astype(np.float64) + 1e-12)

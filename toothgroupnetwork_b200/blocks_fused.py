@@ -101,6 +101,8 @@ def transition_down_fusable(td, p, x, o) -> bool:
         return False
     if _needs_grad(td, p, x):
         return False
+    if td.linear.in_features != 3 + x.shape[1] or td.linear.weight.dtype != torch.float32:
+        return False
     return _bn_ok(td.bn) and td.linear.bias is None and pn2._pw_enabled
 
 

@@ -50,9 +50,22 @@ def dbscan_device(points: torch.Tensor, eps: float = 0.03, min_samples: int = 30
     return labels, core
 
 
+def _as_float32(points: np.ndarray) -> np.ndarray:
+    """The kernel takes float32 coordinates (what ops_utils.get_clustering_labels is handed: float32 points + float32 offsets) and
+    evaluates distances in float64 like scikit-learn.  Wider input is accepted when it holds float32 values; anything else would be
+    clustered on rounded coordinates and could differ from scikit-learn, so it is refused."""
+    points = np.asarray(points)
+    if points.dtype == np.float32:
+        return np.ascontiguousarray(points)
+    down = np.ascontiguousarray(points, dtype=np.float32)
+    if not np.array_equal(down.astype(points.dtype), points):
+        raise L.TgnError(f"dbscan: {points.dtype} coordinates that are not float32 values are not supported")
+    return down
+
+
 def dbscan(points, eps: float = 0.03, min_samples: int = 30) -> Tuple[np.ndarray, np.ndarray]:
     """numpy or tensor (n,3) -> (labels_ int64 (n), core_sample_indices_ int64) like the attributes of a fitted sklearn DBSCAN."""
-    pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float32) if isinstance(points, np.ndarray) else points, dtype=torch.float32)
+    pts = torch.as_tensor(_as_float32(points)) if isinstance(points, np.ndarray) else points.float()
     pts = pts if pts.is_cuda else pts.cuda()
     labels, core = dbscan_device(pts, eps, min_samples)
     both = torch.stack([labels, core.int()]).cpu().numpy()             # one device -> host copy
@@ -85,7 +98,7 @@ def get_clustering_labels(moved_points, labels):
     moved_points = np.asarray(moved_points)
     cond = np.asarray(labels) != 0
     fg = moved_points[cond, :]
-    fg_dev = torch.as_tensor(np.ascontiguousarray(fg, dtype=np.float32)).cuda()
+    fg_dev = torch.as_tensor(_as_float32(fg)).cuda()
     lab_dev, core_dev = dbscan_device(fg_dev, 0.03, 30)
     both = torch.stack([lab_dev, core_dev.int()]).cpu().numpy()
     clustering_labels = both[0].astype(np.int64)
