@@ -86,20 +86,39 @@ def ncu_constants():
 
 
 # ------------------------------------------------------------------------------------------ NUMA
-def numa_bind(local_gpu: int) -> dict:
+def nvml_handle(local_gpu: int):
+    """NVML handle of CUDA device ``local_gpu``: NVML enumerates every GPU of the machine and ignores CUDA_VISIBLE_DEVICES, so
+    the entry of that variable (an index or a GPU-<uuid>) is translated first."""
+    import pynvml
+    pynvml.nvmlInit()
+    vis = [e.strip() for e in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if e.strip()]
+    if local_gpu < len(vis):
+        e = vis[local_gpu]
+        if e.isdigit():
+            return pynvml.nvmlDeviceGetHandleByIndex(int(e))
+        return pynvml.nvmlDeviceGetHandleByUUID(e if isinstance(e, bytes) else e.encode())
+    return pynvml.nvmlDeviceGetHandleByIndex(local_gpu)
+
+
+def sysfs_bdf(domain: int, bus: int, device: int) -> str:
+    return f"{domain:04x}:{bus:02x}:{device:02x}.0"
+
+
+def numa_bind(local_gpu: int, bdf: str = None) -> dict:
     """Bind this process (threads AND future page allocations, i.e. the pinned staging buffers) to the NUMA node of
     its GPU: CPU affinity from /sys/bus/pci/devices/<bdf>/numa_node, memory policy MPOL_PREFERRED through the raw
-    set_mempolicy syscall (no libnuma in the image).  Must run before the host buffers are allocated."""
+    set_mempolicy syscall (no libnuma in the image).  Must run before the host buffers are allocated.  ``bdf`` = the PCI
+    address when the caller knows it (from CUDA); otherwise it is looked up through NVML."""
     info = {"gpu": local_gpu, "node": None, "cpus": None, "mempolicy": None}
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local_gpu)
-        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bdf = bus.lower()
-        if len(bdf.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs uses 4
-            bdf = bdf[4:]
+        if bdf is None:
+            import pynvml
+            bus = pynvml.nvmlDeviceGetPciInfo(nvml_handle(local_gpu)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bdf = bus.lower()
+            if len(bdf.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs uses 4
+                bdf = bdf[4:]
+        info["pci"] = bdf
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
         if node < 0:
             return info
@@ -133,7 +152,7 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.h = nvml_handle(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
@@ -290,6 +309,13 @@ def main():
     numa = {"bound": False} if args.no_numa else numa_bind(local)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    if not args.no_numa:
+        # CUDA's own answer for this device; if the NVML lookup above named another GPU (a remapped device list), bind again --
+        # the pinned staging buffers are allocated further down
+        props = torch.cuda.get_device_properties(local)
+        bdf = sysfs_bdf(props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        if numa.get("pci") != bdf:
+            numa = dict(numa_bind(local, bdf), rebound_from=numa.get("pci"))
     rank, world, local = sharding.init("nccl")
     from toothgroupnetwork_b200 import _lib as L
     from toothgroupnetwork_b200 import pointnet2_utils as pn2
@@ -388,12 +414,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         sharding.barrier()
-    e2e_s = sharding.max_over_ranks(e0.elapsed_time(e1) / 1e3, device)
+    e2e_local_s = e0.elapsed_time(e1) / 1e3
+    e2e_s = sharding.max_over_ranks(e2e_local_s, device)
     e2e_value = world * B * NPOINT * args.steps / e2e_s
 
     # -------- the one collective of the run: per-rank metric records ----------------------------------
     records = sharding.gather_metrics({"sampled_points": B * NPOINT * args.steps, "clouds": B * args.steps, "seconds": local_s,
-                                       "parity_ok": float(parity_ok), "launches": launches}, device)
+                                       "parity_ok": float(parity_ok), "launches": launches,
+                                       "numa_node": float(numa["node"]) if numa.get("node") is not None else -1.0,
+                                       "e2e_seconds": e2e_local_s}, device)
     agg = sharding.reduce_metrics(records)
 
     if rank != 0:
@@ -439,7 +468,8 @@ def main():
                 "d2h_bytes_per_step": int((out_xyz_host.numel() + out_pts_host.numel()) * 4)},
         "gpu_launches": int(agg["launches"]),
         "clocks": clk.summary(),
-        "numa": numa,
+        "numa": dict(numa, per_rank_node=[int(r["numa_node"]) for r in records],
+                     per_rank_e2e_ms_per_step=[round(r["e2e_seconds"] * 1e3 / args.steps, 3) for r in records]),
         "parity_ok": bool(agg["parity_ok"]),
         "parity": {"staged_kernels_equal_public_module": staged_equal, "cloud0_new_xyz_bitwise_vs_oracle": oracle_xyz_bitwise,
                    "cloud0_features_elementwise_rel_vs_oracle": oracle_rel, "floor": "0.05 * max|ref|", "tol": 1e-4},

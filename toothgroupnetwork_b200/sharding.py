@@ -13,7 +13,7 @@ from typing import Dict, List, Sequence
 import torch
 import torch.distributed as dist
 
-METRIC_KEYS = ("sampled_points", "clouds", "seconds", "parity_ok", "launches")
+METRIC_KEYS = ("sampled_points", "clouds", "seconds", "parity_ok", "launches", "numa_node", "e2e_seconds")
 
 
 def env_rank_world() -> tuple:
