@@ -361,7 +361,9 @@ def case_tgn(worlds, feats, labels, timer):
 
 
 def case_tgn_infer(worlds, feats, labels, train_bn, timer):
-    """GroupingNetworkModule forward under torch.no_grad() (the reference's validation / inference step): in the b200 world the
+    """GroupingNetworkModule forward under torch.no_grad() with labels given (the reference's validation step,
+    grouping_network_module.py:25-35,46-57: crops around the ground-truth centroids; the label-free inference branch :58-69 clusters
+    the predicted offsets instead, which needs trained weights -- tests/test_gpu_clustering.py covers that function): in the b200 world the
     PointTransformerLayer and TransitionDown forwards run on the fused kernels (toothgroupnetwork_b200.blocks_fused)."""
     outs, coords, times = {}, {}, {}
     state = None
