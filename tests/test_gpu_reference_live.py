@@ -432,3 +432,49 @@ def test_tgnet_fps_forward_backward_vs_reference():
     assert res["tensors"]["nn_crop_indexes"]["bitwise"]
     assert res["verdict"]["pass"], res["verdict"]
     assert res["grads"]["pass"], res["grads"]
+
+
+def test_tgnet_inference_branch_clusters_and_crops_like_the_reference():
+    """The label-free branch of GroupingNetworkModule.forward (grouping_network_module.py:58-73): predicted offsets are clustered
+    (ops_utils.get_clustering_labels: DBSCAN + noise vote), the centroids pick the 3072-point crops, the second network runs on them.
+    Random weights predict no clusters, so the first network is replaced in BOTH worlds by the same stand-in that 'predicts' the
+    foreground mask and offsets of a nearly converged model; everything after it is the reference's code on either operator set:
+    scikit-learn + KDTree on the host in one world, csrc/dbscan.cu + csrc/crop_knn.cu in the other."""
+    import numpy as np
+    mp = _model_parity()
+    n = 24000
+    xyz, normal, label = clouds.dental_arch(n, 2)
+    lab = torch.where(label < 0, torch.zeros_like(label), label).long()
+    cent = torch.stack([xyz[lab == c].mean(0) if bool((lab == c).any()) else torch.zeros(3) for c in range(int(lab.max()) + 1)])
+    g = torch.Generator().manual_seed(3)
+    offset = 0.93 * (cent[lab] - xyz) + 0.003 * torch.randn(n, 3, generator=g)
+    stray = torch.rand(n, generator=g) < 0.03
+    offset[stray] += 0.08 * torch.randn(int(stray.sum()), 3, generator=g)
+    offset[lab == 0] = 0
+    sem = torch.stack([(lab == 0).float(), (lab != 0).float()]).unsqueeze(0).cuda()          # (1, 2, n) "logits"
+    offset = offset.t().contiguous().unsqueeze(0).cuda()                                     # (1, 3, n)
+    feats = torch.cat([xyz, normal], 1).t().contiguous().unsqueeze(0).cuda()
+
+    class Converged(torch.nn.Module):
+        def forward(self, inputs):
+            return sem, offset, None, None
+
+    outs, state = {}, None
+    for w in (world("reference"), world("b200")):
+        with w, torch.no_grad():
+            torch.manual_seed(0)
+            module = w.mod("models.modules.grouping_network_module").GroupingNetworkModule({"model_parameter": dict(mp.TGN_PARAMS)}).cuda()
+            if state is None:
+                state = {k: v.clone() for k, v in module.state_dict().items()}
+            module.load_state_dict(state)
+            module.eval()
+            module.first_ins_cent_model = Converged()
+            if w.ops == "b200":
+                assert w.mod("ops_utils").get_clustering_labels.__module__ == "toothgroupnetwork_b200.clustering"
+            outs[w.ops] = module([feats])
+    ref, new = outs["reference"], outs["b200"]
+    assert len(ref["nn_crop_indexes"]) == len(new["nn_crop_indexes"]) == 1
+    assert np.array_equal(np.asarray(ref["nn_crop_indexes"][0]), np.asarray(new["nn_crop_indexes"][0]))
+    assert np.asarray(ref["nn_crop_indexes"][0]).shape[0] >= 10                               # the teeth were found
+    assert torch.equal(ref["cropped_feature_ls"], new["cropped_feature_ls"])
+    assert elementwise(new["sem_2"], ref["sem_2"]) < REL_TOL            # (the second network of tgnet_fps has no offset head)
