@@ -215,6 +215,8 @@ class World:
                 from toothgroupnetwork_b200 import clustering, crops
                 crops.accelerate(sys.modules["ops_utils"])
                 clustering.accelerate(sys.modules["ops_utils"])
+                if "models.modules.tsegnet" in sys.modules:
+                    clustering.accelerate_dbscan(sys.modules["models.modules.tsegnet"])
             if ops == "b200" and fused_blocks:
                 # no-grad forwards of PointTransformerLayer / TransitionDown on the fused kernels (autograd keeps the reference's code)
                 from toothgroupnetwork_b200 import blocks_fused

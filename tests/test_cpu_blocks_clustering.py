@@ -69,3 +69,13 @@ def test_clustering_host_helpers():
     assert clustering._as_float32(f32.astype(np.float64)).dtype == np.float32
     with pytest.raises(clustering.L.TgnError):
         clustering._as_float32(f32.astype(np.float64) + 1e-12)
+
+
+def test_dbscan_class_refuses_what_it_does_not_implement():
+    from toothgroupnetwork_b200 import clustering
+    with pytest.raises(clustering.L.TgnError):
+        clustering.DBSCAN(eps=0.1, min_samples=3, metric="manhattan")
+    with pytest.raises(clustering.L.TgnError):
+        clustering.DBSCAN(eps=0.1, min_samples=3).fit(np.zeros((4, 2), np.float32))
+    with pytest.raises(clustering.L.TgnError):                        # no CPU path: the product fails loudly without a GPU
+        clustering.DBSCAN(eps=0.1, min_samples=3).fit(np.zeros((4, 3), np.float32))

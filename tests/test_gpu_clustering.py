@@ -109,3 +109,28 @@ def test_get_clustering_labels_equals_the_reference_function(n, pull, jitter, ou
         want = sklearn_cluster.DBSCAN(eps=0.03, min_samples=30).fit(pts[label != 0]).labels_
         assert (want != -1).all()
     assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+def test_sklearn_shaped_class_on_the_other_call_sites():
+    """tsegnet.py:59 (DBSCAN(eps=0.05, min_samples=3) over a few hundred moved centroid candidates) and
+    ops_utils.clustering_points(method="dbscan") (:28, eps=0.03, min_samples=60)."""
+    rng = np.random.default_rng(5)
+    cand = np.concatenate([rng.normal(c, 0.01, (18, 3)) for c in rng.uniform(-0.5, 0.5, (14, 3))] + [rng.uniform(-0.6, 0.6, (20, 3))]).astype(np.float32)
+    ref = sklearn_cluster.DBSCAN(eps=0.05, min_samples=3).fit(cand, 3)
+    got = clustering.DBSCAN(eps=0.05, min_samples=3).fit(cand, 3)
+    assert np.array_equal(got.labels_, ref.labels_) and np.array_equal(got.core_sample_indices_, ref.core_sample_indices_)
+    assert np.array_equal(got.components_, ref.components_)
+    assert np.array_equal(clustering.DBSCAN(eps=0.05, min_samples=3).fit_predict(cand), ref.labels_)
+    from oracle import ref_models
+    if ref_models.reference_root() is None:
+        pytest.skip("reference checkout not staged")
+    pts, label = moved_cloud(24000, 4, 0.9, 0.004)
+    moved = [pts[label != 0], pts[label != 0][::2]]
+    with ref_models.World("reference") as w:
+        want = w.mod("ops_utils").clustering_points(moved, "dbscan")
+    with ref_models.World("b200") as w:
+        assert w.mod("ops_utils").DBSCAN is clustering.DBSCAN and w.mod("models.modules.tsegnet").DBSCAN is clustering.DBSCAN
+        got = w.mod("ops_utils").clustering_points(moved, "dbscan")
+    for a, b in zip(want, got):                                       # centroids, centroid labels, per-point labels
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))

@@ -66,10 +66,37 @@ def _as_float32(points: np.ndarray) -> np.ndarray:
 def dbscan(points, eps: float = 0.03, min_samples: int = 30) -> Tuple[np.ndarray, np.ndarray]:
     """numpy or tensor (n,3) -> (labels_ int64 (n), core_sample_indices_ int64) like the attributes of a fitted sklearn DBSCAN."""
     pts = torch.as_tensor(_as_float32(points)) if isinstance(points, np.ndarray) else points.float()
+    if not pts.is_cuda and not torch.cuda.is_available():
+        raise L.TgnError("dbscan needs a CUDA device (there is no CPU path)")
     pts = pts if pts.is_cuda else pts.cuda()
     labels, core = dbscan_device(pts, eps, min_samples)
     both = torch.stack([labels, core.int()]).cpu().numpy()             # one device -> host copy
     return both[0].astype(np.int64), np.flatnonzero(both[1]).astype(np.int64)
+
+
+class DBSCAN:
+    """The slice of ``sklearn.cluster.DBSCAN`` the reference uses -- ``DBSCAN(eps=..., min_samples=...).fit(X, y)`` then
+    ``.labels_`` / ``.core_sample_indices_`` / ``.components_`` -- on csrc/dbscan.cu: ops_utils.py:28,98, tsegnet.py:59,
+    inference_pipeline_tsegnet.py:39.  Euclidean metric only, which is all the reference asks for."""
+
+    def __init__(self, eps: float = 0.5, *, min_samples: int = 5, metric: str = "euclidean", **unsupported):
+        if metric != "euclidean" or any(v is not None for v in unsupported.values()):
+            raise L.TgnError(f"DBSCAN: only the Euclidean metric with default options is implemented (got metric={metric!r}, {unsupported})")
+        self.eps, self.min_samples = eps, min_samples
+
+    def fit(self, X, y=None, sample_weight=None):
+        if sample_weight is not None:
+            raise L.TgnError("DBSCAN: sample_weight is not implemented")
+        X = np.asarray(X)
+        if X.ndim != 2 or X.shape[1] != 3:
+            raise L.TgnError(f"DBSCAN: expected (n, 3) points, got {X.shape}")
+        self.labels_, self.core_sample_indices_ = dbscan(X, self.eps, self.min_samples)
+        self.components_ = X[self.core_sample_indices_].copy()
+        self.n_features_in_ = 3
+        return self
+
+    def fit_predict(self, X, y=None, sample_weight=None):
+        return self.fit(X, y, sample_weight).labels_
 
 
 def _explained_variance(points: np.ndarray) -> np.ndarray:
@@ -95,6 +122,8 @@ def _majority(rows: np.ndarray) -> np.ndarray:
 def get_clustering_labels(moved_points, labels):
     """Drop-in for ops_utils.get_clustering_labels (:86-144): moved_points (N,3), labels (N,) or (N,1) semantic classes ->
     cluster label of every foreground point (labels != 0), int64."""
+    if not torch.cuda.is_available():
+        raise L.TgnError("get_clustering_labels needs a CUDA device (there is no CPU path)")
     moved_points = np.asarray(moved_points)
     cond = np.asarray(labels) != 0
     fg = moved_points[cond, :]
@@ -133,5 +162,14 @@ def get_clustering_labels(moved_points, labels):
 
 
 def accelerate(ops_utils_module) -> None:
-    """Swap ops_utils.get_clustering_labels of an imported reference module for the device version."""
+    """Swap ops_utils.get_clustering_labels of an imported reference module for the device version, and the ``DBSCAN`` name the module
+    imported from scikit-learn (``clustering_points(method="dbscan")``, ops_utils.py:28) for the class above."""
     ops_utils_module.get_clustering_labels = get_clustering_labels
+    accelerate_dbscan(ops_utils_module)
+
+
+def accelerate_dbscan(module) -> None:
+    """Point a module's ``DBSCAN`` name (``from sklearn.cluster import DBSCAN`` in ops_utils.py, models/modules/tsegnet.py,
+    inference_pipelines/inference_pipeline_tsegnet.py) at the device implementation."""
+    if hasattr(module, "DBSCAN"):
+        module.DBSCAN = DBSCAN

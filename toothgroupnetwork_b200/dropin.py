@@ -62,6 +62,9 @@ def accelerate_ops_utils(ops_utils_module=None) -> None:
         ops_utils_module = importlib.import_module("ops_utils")
     crops.accelerate(ops_utils_module)
     clustering.accelerate(ops_utils_module)        # DBSCAN + noise vote of get_clustering_labels (ops_utils.py:86-144)
+    for name in ("models.modules.tsegnet", "inference_pipelines.inference_pipeline_tsegnet"):
+        if name in sys.modules:                     # their own ``from sklearn.cluster import DBSCAN`` (tsegnet.py:7,59)
+            clustering.accelerate_dbscan(sys.modules[name])
 
 
 def accelerate_blocks(blocks_module=None) -> None:
