@@ -8,6 +8,15 @@ soon as they have landed, and results return on a third stream (PCIe is full dup
     pipe = HostPipeline(sa_module, chunk_clouds=148, n_streams=2)
     pipe(host_feats, out_xyz_host, out_points_host)      # all pinned; returns after a full sync
 
+For a STREAM of batches (a loader handing over one pinned batch after another) the copies of batch i+1 need not wait for batch i:
+
+    for batch in loader:
+        pipe.submit(batch, out_xyz_host, out_points_host)   # returns at once; H2D of this batch overlaps the previous batch's kernels
+    pipe.drain()
+
+``submit`` runs the module over the WHOLE batch (the kernel shapes of the device-resident path, 8 clouds per SM) from one of two
+device input buffers; the copy of the next batch lands in the other one meanwhile, results return on a third stream.
+
 ``host_feats`` is the reference's model input layout ``(B, C, N)`` with xyz in channels 0..2
 (``models/modules/pointnet_pp.py:43-47``: ``l0_xyz = xyz[:, :3, :]``).
 """
@@ -42,6 +51,7 @@ class HostPipeline:
         self.copy_in = torch.cuda.Stream()
         self.copy_out = torch.cuda.Stream()
         self._dev = None
+        self._ring, self._ring_free, self._submitted, self._last = None, [None, None], 0, None
 
     def _plan(self, B: int):
         """[(lo, hi)] of the chunks and [(first_chunk, last_chunk)] of the compute groups."""
@@ -106,3 +116,61 @@ class HostPipeline:
         main.wait_stream(self.copy_in)
         for s in self.streams:
             main.wait_stream(s)
+
+    @torch.no_grad()
+    def submit(self, host_feats: torch.Tensor, out_xyz_host: torch.Tensor, out_points_host: torch.Tensor) -> torch.cuda.Event:
+        """Queue one whole batch: H2D into the free one of two device buffers (copy stream), the module over the full batch (compute
+        stream) once it has landed, D2H of the results (third stream).  Nothing here waits for the previous batch except the reuse of
+        a device buffer (two batches back) and the order of the result copies, so consecutive calls overlap copy and compute across
+        batches.  Returns the event that marks this batch's results complete in the host buffers; the caller must not reuse
+        ``host_feats`` before the copy has been consumed (``drain()`` or the event of the NEXT submit's results is enough)."""
+        if self._ring is None or self._ring[0].shape != host_feats.shape:
+            self._ring = [torch.empty(host_feats.shape, dtype=host_feats.dtype, device="cuda") for _ in range(2)]
+            self._ring_free, self._submitted = [None, None], 0
+        if self._submitted == 0:                                  # first batch after idle: order behind whatever the caller queued
+            main = torch.cuda.current_stream()
+            self.copy_in.wait_stream(main)
+            self.streams[0].wait_stream(main)
+            self.copy_out.wait_stream(main)
+        slot = self._submitted % 2
+        self._submitted += 1
+        dev = self._ring[slot]
+        if self._ring_free[slot] is not None:
+            self.copy_in.wait_event(self._ring_free[slot])        # the batch two back has been read
+        with torch.cuda.stream(self.copy_in):
+            dev.copy_(host_feats, non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(self.copy_in)
+        s = self.streams[0]
+        s.wait_event(landed)
+        saved_mode, saved_engine = pn2._fps_mode, pn2._sa_engine
+        if self.sa_engine is not None:
+            pn2.set_sa_engine(self.sa_engine)
+        pn2.set_fps_mode(self.fps_mode if self.fps_mode is not None else 0)
+        with torch.cuda.stream(s):
+            new_xyz, new_points = self.module(dev[:, :3].contiguous(), dev)
+            if not new_xyz.is_contiguous():
+                new_xyz = pn2.transpose_last2(new_xyz.permute(0, 2, 1))
+            done = torch.cuda.Event()
+            done.record(s)
+        pn2.set_fps_mode(saved_mode)
+        pn2.set_sa_engine(saved_engine)
+        self._ring_free[slot] = done
+        self.copy_out.wait_event(done)
+        new_xyz.record_stream(self.copy_out)
+        new_points.record_stream(self.copy_out)
+        with torch.cuda.stream(self.copy_out):
+            out_xyz_host.copy_(new_xyz, non_blocking=True)
+            out_points_host.copy_(new_points, non_blocking=True)
+            fin = torch.cuda.Event()
+            fin.record(self.copy_out)
+        self._last = fin
+        return fin
+
+    def drain(self) -> None:
+        """Make the current stream wait for every submitted batch (results in their host buffers); the next submit starts a new run."""
+        main = torch.cuda.current_stream()
+        main.wait_stream(self.copy_in)
+        main.wait_stream(self.streams[0])
+        main.wait_stream(self.copy_out)
+        self._submitted, self._ring_free = 0, [None, None]
